@@ -1,0 +1,163 @@
+/* vmmt.h -- C ABI of libvmmt.so: the sm_100a kernels behind the VI-model-1 hot path.
+ *
+ * The reference (iacercalixto/variational_mmt) is pure Python over PyTorch and has no FFI of its own:
+ * every entry point below replaces one or more torch library calls made by the reference modules
+ * (cited per function as file:line relative to the reference root).  The Python host
+ * (variational_mmt_b200/_lib.py) binds these with ctypes and passes tensor.data_ptr() values and the
+ * current CUDA stream; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - all floating-point buffers are fp32 device memory owned by the caller (PyTorch); kernels never
+ *     allocate or free; token ids / lengths are int64 device memory, as the reference holds them;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and is CUDA-graph capturable;
+ *   - return value 0 = ok; > 0 = cudaError_t; < 0 = VMMT_E*; vmmt_last_error() has the message
+ *     (thread-local).  There is no CPU fallback of any kind.
+ *   - sequence tensors are time-major [T, B, *], the layout the reference's RNN code uses.
+ */
+#ifndef VMMT_H_
+#define VMMT_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VMMT_ACT_NONE = 0, VMMT_ACT_RELU = 1, VMMT_ACT_TANH = 2, VMMT_ACT_SOFTPLUS = 3, VMMT_ACT_SIGMOID = 4 };
+
+const char* vmmt_last_error(void);
+int vmmt_version(void);
+/* number of kernels libvmmt has launched in this process (bench.py's gpu_launches). */
+unsigned long long vmmt_launch_count(void);
+/* 0 = auto (tcgen05 TF32 tensor-core GEMM where eligible), 1 = exact-fp32 SIMT GEMM everywhere. */
+void vmmt_set_gemm_mode(int mode);
+int vmmt_get_gemm_mode(void);
+
+/* C[M,N] (ldc) = act(op(A) op(B) + bias[N]) (+C if accumulate).
+ * a_kmajor: A stored [M,K] (1) or [K,M] (0);  b_kmajor: B stored [N,K] (1, nn.Linear weight) or [K,N] (0).
+ * Replaces nn.Linear / torch.mm / addmm on the path: GlobalAttention.py:71,78,113,188;
+ * NormalVariationalEncoder.py:18-25,35-43; the input projections inside nn.LSTM (Models.py:124-129). */
+int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
+              float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
+              void* stream);
+
+/* Embedding gather / dense scatter-add (Embeddings.py:169-188; nn.Embedding padding_idx row gets no grad). */
+int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int E, float* out, void* stream);
+int vmmt_embedding_bwd(const int64_t* idx, int64_t n, const float* dout, int E, int64_t pad_idx,
+                       float* dtable, void* stream);
+
+/* ---- LSTM recurrence, one layer, one or two directions per launch (nn.LSTM: Models.py:124-149,
+ * 892-893; VI_Model1.py:106).  gx = x W_ih^T (no bias) is computed by vmmt_gemm beforehand. */
+typedef struct VmmtLstmDir {
+  const float* gx;       /* [T,N,4H] */
+  const float* w_hh;     /* [4H,H]  gate order i,f,g,o */
+  const float* b_ih;     /* [4H] or NULL */
+  const float* b_hh;     /* [4H] or NULL */
+  const float* rowbias;  /* [N,4H] or NULL: per-example additive term (decoder: z W_ih[:,E:]^T) */
+  const float* h0;       /* [N,H] or NULL (zeros) */
+  const float* c0;       /* [N,H] or NULL */
+  float* out;            /* out[(t*N+n)*out_ld + u]; zero past lengths[n] */
+  int64_t out_ld;
+  float* hT;             /* [N,H] or NULL: state at each row's last valid step */
+  float* cT;
+  float* gates;          /* [T,N,4H] activated gates saved for backward, or NULL (inference) */
+  float* cs;             /* [T,N,H] cell states saved for backward, or NULL */
+  int32_t reverse;       /* 1: run t = T-1 .. 0 */
+  int32_t pad_;
+} VmmtLstmDir;
+
+typedef struct VmmtLstmDirBwd {
+  const float* w_hh;     /* [4H,H] */
+  const float* gates;    /* saved by forward */
+  const float* cs;
+  const float* c0;       /* or NULL */
+  const float* dout;     /* dL/dout, dout[(t*N+n)*dout_ld + u], or NULL */
+  int64_t dout_ld;
+  const float* dhT;      /* [N,H] or NULL */
+  const float* dcT;
+  float* dgates;         /* [T,N,4H] OUT: gradient wrt the pre-activation gates (= d gx) */
+  float* dh0;            /* [N,H] OUT or NULL */
+  float* dc0;
+  int32_t reverse;
+  int32_t pad_;
+} VmmtLstmDirBwd;
+
+size_t vmmt_lstm_workspace_bytes(int ndir, int N, int H);
+int vmmt_lstm_seq_supported(int ndir, int N, int H);
+int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
+                      void* stream);
+/* single-step cell on pre-summed gate pre-activations (decode with large sentences x beam). */
+int vmmt_lstm_cell_fwd(const float* gates_pre, const float* b_ih, const float* b_hh, const float* rowbias,
+                       const float* c_prev, float* h_out, float* c_out, int N, int H, void* stream);
+
+/* ---- GlobalAttention core (GlobalAttention.py:108-113,169-184): qp = linear_in(q) [T,B,H],
+ * ctx [S,B,H] -> align [T,B,S] (masked softmax), cvec [T,B,H].  S <= 128. */
+int vmmt_attention_fwd(const float* qp, const float* ctx, const int64_t* lengths, float* align,
+                       float* cvec, int T, int B, int S, int H, void* stream);
+int vmmt_attention_bwd(const float* dcvec, const float* qp, const float* ctx, const float* align,
+                       const int64_t* lengths, float* dscore_ws /*[T,B,S]*/, float* dqp, float* dctx,
+                       int accumulate_dctx, int T, int B, int S, int H, void* stream);
+
+/* ---- inference networks (NormalVariationalEncoder.py:65-84, 12-43; Dists.py:21-26; VILoss.py:439-460) */
+int vmmt_masked_mean_fwd(const float* x, const int64_t* lengths, float* out, int64_t out_ld, int T, int B,
+                         int H, void* stream);
+int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* lengths, float* dx,
+                         int accumulate, int T, int B, int H, void* stream);
+int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
+int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, void* stream);
+int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
+int vmmt_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int vmmt_normal_sample(const float* mu, const float* sd, const float* eps /*or NULL: Philox*/, float* z,
+                       int64_t n, uint64_t seed, uint64_t offset, void* stream);
+int vmmt_kl_fwd(const float* mu_q, const float* sd_q, const float* mu_p /*NULL: 0*/,
+                const float* sd_p /*NULL: 1*/, float* out1, int B, int Z, void* stream);
+int vmmt_kl_bwd(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, float* dmu_q,
+                float* dsd_q, float* dmu_p /*or NULL*/, float* dsd_p /*or NULL*/,
+                const float* gscale /*device scalar or NULL*/, float scale, int B, int Z, void* stream);
+
+/* ---- image-feature head (NormalVariationalEncoder.py:286-299) and its loss (VILoss.py:22-56,317-332) */
+int vmmt_gate_fwd(const float* z, const float* w, const float* bias, float* gate /*[B]*/, float* gated,
+                  int B, int Z, void* stream);
+int vmmt_gate_bwd(const float* dgated, const float* z, const float* gate, float* dpre_ws /*[B]*/, float* dw,
+                  float* db, int B, int Z, void* stream);
+int vmmt_image_loss_fwd(const float* loc, const float* v, float* rowstats /*[B,4]*/,
+                        float* out2 /*{logprob, cosine}*/, int B, int D, void* stream);
+int vmmt_image_loss_bwd(const float* loc, const float* v, const float* rowstats, float* dloc,
+                        const float* gscale /*device scalar or NULL*/, float scale, int legacy_passthrough,
+                        int B, int D, void* stream);
+
+/* ---- generator + criterion (ModelConstructor.py:582-585; VILoss.py:228,243,515-531) */
+size_t vmmt_generator_workspace_bytes(int M, int V);
+int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b, const int64_t* target,
+                           int64_t pad_idx, int M, int H, int V, float* lse /*[M]*/,
+                           float* stats3 /*{nll_sum, n_words, n_correct}*/, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int vmmt_generator_nll_bwd(const float* x, const float* W, const float* b, const int64_t* target,
+                           int64_t pad_idx, const float* lse, const float* gscale /*device scalar or NULL*/,
+                           float scale, int M, int H, int V,
+                           float* dx /*or NULL*/, float* dW /*accumulated*/, float* db /*accumulated*/,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H, int V,
+                            float* out /*[M,V]*/, float* lse_ws /*[M]*/, void* stream);
+
+/* ---- optimiser: global-norm clip + Adam on flat buffers (Optim.py:69-70,94-96) */
+size_t vmmt_sqnorm_workspace_bytes(void);
+int vmmt_sqnorm(const float* g, int64_t n, float* out1, int accumulate, void* workspace, void* stream);
+int vmmt_adam_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* sqnorm /*device scalar*/, float max_norm, float grad_scale, float lr,
+                        float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/* ---- beam search bookkeeping (Beam.py:64-123; Models.py:589-594) */
+int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, int64_t eos, float* scores,
+                      int64_t* next_ys, int32_t* prev_ks, float* fin_score, int32_t* fin_t, int32_t* fin_k,
+                      int32_t* n_fin, int32_t* done, int32_t* n_active, void* stream);
+int vmmt_beam_reorder(const float* src, float* dst, const int32_t* prev_k_step, const int32_t* done, int L,
+                      int K, int B, int H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMMT_H_ */

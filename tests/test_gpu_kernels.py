@@ -1,0 +1,21 @@
+"""-m gpu: per-kernel checks of the libvmmt C ABI against plain torch math (tests/kernel_checks.py)."""
+import pytest
+
+import kernel_checks as kc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["fp32_simt", "tf32_tc"])
+def gemm_mode(request, cuda_device):
+    from variational_mmt_b200 import _lib
+    _lib.lib.vmmt_set_gemm_mode(1 if request.param == "fp32_simt" else 0)
+    yield 1.0 if request.param == "fp32_simt" else 100.0     # TF32 operands: ~1e-3 relative
+    _lib.lib.vmmt_set_gemm_mode(0)
+
+
+@pytest.mark.parametrize("group", [n for n, _ in kc.ALL])
+def test_kernel_group(group, gemm_mode):
+    fn = dict(kc.ALL)[group]
+    bad = [(l, e, t) for l, e, t in fn() if not (e <= t * gemm_mode or (t == 0.0 and e == 0.0))]
+    assert not bad, "\n".join(f"{l}: err {e:.3e} > tol {t * gemm_mode:.1e}" for l, e, t in bad)

@@ -1,0 +1,36 @@
+"""StdRNNVIModel1Decoder (reference: onmt/VI_Model1.py:17-159)."""
+import torch
+
+from . import ops
+from .Models import RNNVIDecoderBase
+from .modules import LSTM
+
+
+class StdRNNVIModel1Decoder(RNNVIDecoderBase):
+    """Attention decoder whose LSTM input is [embedding ; z].  The concatenation is algebraic here:
+    z W_ih[:, E:]^T is computed once per batch and enters layer 0 as a per-example gate bias."""
+
+    def __init__(self, *args, **kwargs):
+        self.multimodal_model_type = "vi-model1"
+        super().__init__(*args, **kwargs)
+
+    def _run_forward_pass(self, input, context, state, context_lengths=None, **kwargs):
+        assert "z_sample" in kwargs and "image_features" in kwargs, \
+            "Must provide the following parameters in kwargs: ['z_sample', 'image_features']"
+        z_sample = kwargs["z_sample"]
+        assert kwargs["image_features"] is None, "Model 'vi-model1' does not use image features in the decoder!"
+        emb = self.embeddings(input)                                           # [T,B,E]
+        E = self.embeddings.embedding_size
+        w0 = self.rnn.weight_ih_l0
+        zb = ops.linear(z_sample.detach(), w0, cols=(E, E + self.latent_dim))     # [B,4H]
+        rnn_output, hidden = self.rnn(emb, state.hidden, in_bias=zb, in_cols=(0, E))
+        attn_h, align = self.attn.forward_time_major(rnn_output, context, context_lengths)
+        outputs = ops.dropout(attn_h, self.dropout_p, self.training)
+        return hidden, outputs, {"std": align}, None
+
+    def _build_rnn(self, rnn_type, input_size, hidden_size, num_layers, dropout):
+        return LSTM(input_size + self.latent_dim, hidden_size, num_layers=num_layers, dropout=dropout)
+
+    @property
+    def _input_size(self):
+        return self.embeddings.embedding_size

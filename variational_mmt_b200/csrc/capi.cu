@@ -1,0 +1,75 @@
+// C-ABI plumbing: error reporting, device queries, GEMM dispatch.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include "common.cuh"
+#include "vmmt_internal.h"
+
+namespace {
+thread_local char g_err[512] = "";
+std::mutex g_mu;
+int g_sms[64];
+bool g_sms_init = false;
+int g_gemm_mode = -1;   // -1 unread, 0 = auto (tcgen05 when eligible), 1 = force SIMT fp32
+}
+
+void vmmt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static unsigned long long g_launches = 0;
+extern "C" unsigned long long vmmt_launch_count(void) { return g_launches; }
+
+int vmmt_check_launch(const char* what) {
+  ++g_launches;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    vmmt_set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return VMMT_OK;
+}
+
+int vmmt_num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_sms_init) { memset(g_sms, 0, sizeof(g_sms)); g_sms_init = true; }
+  if (g_sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sms[dev] = n;
+  }
+  return g_sms[dev];
+}
+
+extern "C" const char* vmmt_last_error(void) { return g_err; }
+extern "C" int vmmt_version(void) { return 100; }
+
+// 0 = auto, 1 = exact-fp32 SIMT everywhere (parity debugging; also env VMMT_GEMM=simt)
+extern "C" void vmmt_set_gemm_mode(int mode) { g_gemm_mode = mode; }
+extern "C" int vmmt_get_gemm_mode(void) {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("VMMT_GEMM");
+    g_gemm_mode = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return g_gemm_mode;
+}
+
+extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb,
+                         int b_kmajor, float* C, int64_t ldc, int M, int N, int K, const float* bias,
+                         int act, int accumulate, void* stream) {
+  VMMT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dims");
+  VMMT_REQUIRE(A && B && C, "gemm: null operand");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vmmt_get_gemm_mode() == 0 &&
+      vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K)) {
+    return vmmt_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);
+  }
+  return vmmt_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);
+}

@@ -1,0 +1,166 @@
+// Batched prior-only beam search step kernels (device-side beam bookkeeping) and the single-step
+// LSTM cell used when the batch (sentences x beam) is too large for the persistent kernel.
+//
+// Reference: onmt/translate/Beam.py:64-123 (advance), onmt/Models.py:589-594 (beam_update),
+// onmt/translate/TranslatorMultimodalVI.py:163-218 (the step loop).  Rows are beam-major
+// (row = k*B + b).  alpha = beta = 0 (opts.py:425-429): hypothesis score = summed
+// log-prob.  A sentence is frozen once Beam.done() holds for it (the reference decodes one
+// sentence per call, so nothing is ever advanced past that point).
+#include "common.cuh"
+#include "vmmt_internal.h"
+
+namespace {
+
+constexpr int KMAX = 8;
+
+struct Cand { float v; int i; };
+__device__ __forceinline__ bool better(float v, int i, float w, int j) {
+  return v > w || (v == w && i < j);
+}
+
+// One CTA per sentence.  logp [K*B, V] -> top-K of the flattened [K*V] candidate scores.
+__global__ void __launch_bounds__(256)
+beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int step, int64_t eos,
+                    float* __restrict__ scores,        // [B,K] running hypothesis scores (in/out)
+                    int64_t* __restrict__ next_ys,     // [Lmax+1, K, B] tokens; slice `step` is the input
+                    int32_t* __restrict__ prev_ks,     // [Lmax, K, B] back pointers
+                    float* __restrict__ fin_score,     // [B] best finished score
+                    int32_t* __restrict__ fin_t, int32_t* __restrict__ fin_k,   // [B]
+                    int32_t* __restrict__ n_fin, int32_t* __restrict__ done,    // [B]
+                    int32_t* __restrict__ n_active) {
+  const int b = blockIdx.x;
+  if (done[b]) return;
+  __shared__ Cand cand[256 * KMAX];
+  __shared__ Cand best[KMAX];
+  __shared__ float rv[8];
+  __shared__ int ri[8], rp[8];
+  const int tid = threadIdx.x;
+  Cand loc[KMAX];
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q) { loc[q].v = -INFINITY; loc[q].i = 0x7fffffff; }
+  const int nbeam = (step == 0) ? 1 : K;               // Beam.py:93-94: first step uses beam row 0 only
+  for (int k = 0; k < nbeam; ++k) {
+    const float base = (step == 0) ? 0.f : scores[b * K + k];
+    const bool dead = step > 0 && next_ys[((size_t)step * K + k) * B + b] == eos;   // Beam.py:89-92
+    const float* row = logp + ((size_t)k * B + b) * V;
+    for (int j = tid; j < V; j += blockDim.x) {
+      const float v = dead ? -1e20f : row[j] + base;
+      const int id = k * V + j;
+      if (better(v, id, loc[K - 1].v, loc[K - 1].i)) {
+        loc[K - 1].v = v; loc[K - 1].i = id;
+#pragma unroll
+        for (int q = KMAX - 1; q > 0; --q)
+          if (q < K && better(loc[q].v, loc[q].i, loc[q - 1].v, loc[q - 1].i)) {
+            const Cand tmp = loc[q]; loc[q] = loc[q - 1]; loc[q - 1] = tmp;
+          }
+      }
+    }
+  }
+  for (int q = 0; q < K; ++q) cand[tid * KMAX + q] = loc[q];
+  __syncthreads();
+  // K rounds of block-wide arg-max over the 256*K local winners
+  for (int r = 0; r < K; ++r) {
+    float bv = -INFINITY; int bi = 0x7fffffff, bp = -1;
+    for (int q = 0; q < K; ++q) {
+      const Cand c = cand[tid * KMAX + q];
+      if (c.i != 0x7fffffff && better(c.v, c.i, bv, bi)) { bv = c.v; bi = c.i; bp = tid * KMAX + q; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bp = op; }
+    }
+    if ((tid & 31) == 0) { rv[tid >> 5] = bv; ri[tid >> 5] = bi; rp[tid >> 5] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (better(rv[w], ri[w], rv[0], ri[0])) { rv[0] = rv[w]; ri[0] = ri[w]; rp[0] = rp[w]; }
+      best[r].v = rv[0]; best[r].i = ri[0];
+      if (rp[0] >= 0) cand[rp[0]].i = 0x7fffffff;        // remove the winner
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int nf = n_fin[b];
+    for (int k = 0; k < K; ++k) {
+      const int pk = best[k].i / V, tok = best[k].i - pk * V;
+      scores[b * K + k] = best[k].v;
+      prev_ks[((size_t)step * K + k) * B + b] = pk;
+      next_ys[((size_t)(step + 1) * K + k) * B + b] = tok;
+      if (tok == (int)eos) {                              // Beam.py:112-118
+        if (nf == 0 || best[k].v > fin_score[b]) { fin_score[b] = best[k].v; fin_t[b] = step + 1; fin_k[b] = k; }
+        ++nf;
+      }
+    }
+    n_fin[b] = nf;
+    const int pk0 = best[0].i / V;
+    if (best[0].i - pk0 * V == (int)eos && nf >= 1) {     // eos_top and n_best finished -> done()
+      done[b] = 1;
+      atomicSub(n_active, 1);
+    }
+  }
+}
+
+// new[l, k*B+b, :] = old[l, prev_k[k,b]*B + b, :]   (DecoderState.beam_update)
+__global__ void beam_reorder_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                    const int32_t* __restrict__ prev_k, const int32_t* __restrict__ done,
+                                    int L, int K, int B, int H) {
+  const int r = blockIdx.x;           // destination row in [0, K*B)
+  const int l = blockIdx.y;
+  const int k = r / B, b = r % B;
+  const int pk = done[b] ? k : prev_k[(size_t)k * B + b];
+  const float* s = src + ((size_t)l * K * B + (size_t)pk * B + b) * H;
+  float* d = dst + ((size_t)l * K * B + r) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) d[i] = s[i];
+}
+
+// single-step cell: G = gpre + biases (+rowbias); c' = f c + i g; h' = o tanh(c')
+__global__ void lstm_cell_kernel(const float* __restrict__ gpre, const float* __restrict__ b_ih,
+                                 const float* __restrict__ b_hh, const float* __restrict__ rowbias,
+                                 const float* __restrict__ c_prev, float* __restrict__ h_out,
+                                 float* __restrict__ c_out, int N, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * H) return;
+  const int n = i / H, u = i % H;
+  float G[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const size_t j = (size_t)g * H + u;
+    G[g] = gpre[(size_t)n * 4 * H + j] + (b_ih ? b_ih[j] : 0.f) + (b_hh ? b_hh[j] : 0.f) +
+           (rowbias ? rowbias[(size_t)n * 4 * H + j] : 0.f);
+  }
+  const float ig = sigmoidf_(G[0]), fg = sigmoidf_(G[1]), gg = tanhf(G[2]), og = sigmoidf_(G[3]);
+  const float c = fg * c_prev[i] + ig * gg;
+  c_out[i] = c;
+  h_out[i] = og * tanhf(c);
+}
+
+}  // namespace
+
+extern "C" int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, int64_t eos,
+                                 float* scores, int64_t* next_ys, int32_t* prev_ks, float* fin_score,
+                                 int32_t* fin_t, int32_t* fin_k, int32_t* n_fin, int32_t* done,
+                                 int32_t* n_active, void* stream) {
+  VMMT_REQUIRE(K >= 1 && K <= KMAX, "beam_advance: beam size %d outside [1,%d]", K, KMAX);
+  beam_advance_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logp, B, K, V, step, eos, scores, next_ys,
+                                                          prev_ks, fin_score, fin_t, fin_k, n_fin,
+                                                          done, n_active);
+  return vmmt_check_launch("beam_advance");
+}
+
+extern "C" int vmmt_beam_reorder(const float* src, float* dst, const int32_t* prev_k_step,
+                                 const int32_t* done, int L, int K, int B, int H, void* stream) {
+  beam_reorder_kernel<<<dim3(K * B, L), 128, 0, (cudaStream_t)stream>>>(src, dst, prev_k_step, done, L,
+                                                                        K, B, H);
+  return vmmt_check_launch("beam_reorder");
+}
+
+extern "C" int vmmt_lstm_cell_fwd(const float* gates_pre, const float* b_ih, const float* b_hh,
+                                  const float* rowbias, const float* c_prev, float* h_out,
+                                  float* c_out, int N, int H, void* stream) {
+  lstm_cell_kernel<<<ceil_div((int64_t)N * H, 256), 256, 0, (cudaStream_t)stream>>>(
+      gates_pre, b_ih, b_hh, rowbias, c_prev, h_out, c_out, N, H);
+  return vmmt_check_launch("lstm_cell");
+}

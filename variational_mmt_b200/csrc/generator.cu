@@ -1,0 +1,155 @@
+// Generator = Linear(H,V) + LogSoftmax fused with the NLL criterion and the accuracy statistics.
+//
+// Reference: onmt/ModelConstructor.py:582-585 (generator), onmt/VILoss.py:228,243 (scores, NLLLoss
+// with weight[pad]=0, size_average=False), onmt/VILoss.py:515-531 (_stats: argmax accuracy over
+// non-pad targets).
+//
+// forward : logits tile -> per-row log-sum-exp, target log-prob, argmax  => {nll_sum, n_words,
+//           n_correct}; log-probabilities are never written out.
+// backward: dlogits = (softmax - onehot) * [tgt != pad] * scale, then dX = dlogits W,
+//           dW += dlogits^T X, db += colsum(dlogits).  The logits are recomputed from (x, W, lse),
+//           nothing of size M x V is saved between forward and backward.
+// decode  : vmmt_generator_logprobs materialises log-probs [M,V] (beam search needs them).
+#include "common.cuh"
+#include "vmmt_internal.h"
+
+namespace {
+
+// one CTA per row of logits [M,V]
+__global__ void __launch_bounds__(256)
+row_lse_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int64_t pad,
+               float* __restrict__ lse, float* __restrict__ rowstat, int V) {
+  __shared__ float smax[8];
+  __shared__ int sarg[8];
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const float* l = logits + (size_t)row * V;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    const float v = l[j];
+    if (v > mx) { mx = v; arg = j; }          // strided scan keeps the smallest index per thread
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { smax[w] = mx; sarg[w] = arg; }
+  __syncthreads();
+  mx = smax[0]; arg = sarg[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+    if (smax[i] > mx || (smax[i] == mx && sarg[i] < arg)) { mx = smax[i]; arg = sarg[i]; }
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf(l[j] - mx);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float L = mx + logf(s);
+    lse[row] = L;
+    if (rowstat) {
+      const int64_t tg = target[row];
+      const bool on = tg != pad;
+      rowstat[row * 3 + 0] = on ? (L - l[tg]) : 0.f;      // -log p(target)
+      rowstat[row * 3 + 1] = on ? 1.f : 0.f;
+      rowstat[row * 3 + 2] = (on && arg == (int)tg) ? 1.f : 0.f;
+    }
+  }
+}
+
+// deterministic single-block reduction of the per-row statistics
+__global__ void reduce_rowstat_kernel(const float* __restrict__ rowstat, int M, float* __restrict__ out) {
+  __shared__ float red[32];
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    a += rowstat[i * 3]; b += rowstat[i * 3 + 1]; c += rowstat[i * 3 + 2];
+  }
+  a = block_sum(a, red); b = block_sum(b, red); c = block_sum(c, red);
+  if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = c; }
+}
+
+__global__ void dlogits_kernel(float* __restrict__ logits, const float* __restrict__ lse,
+                               const int64_t* __restrict__ target, int64_t pad,
+                               const float* __restrict__ gscale, float scale, int V) {
+  if (gscale) scale *= gscale[0];
+  const int row = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= V) return;
+  const int64_t tg = target[row];
+  float* p = logits + (size_t)row * V + j;
+  float g = 0.f;
+  if (tg != pad) g = (expf(*p - lse[row]) - (j == (int)tg ? 1.f : 0.f)) * scale;
+  *p = g;
+}
+
+__global__ void logprob_kernel(float* __restrict__ logits, const float* __restrict__ lse, int V) {
+  const int row = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < V) logits[(size_t)row * V + j] -= lse[row];
+}
+
+}  // namespace
+
+extern "C" int vmmt_gemm(const float*, int64_t, int, const float*, int64_t, int, float*, int64_t,
+                         int, int, int, const float*, int, int, void*);
+
+extern "C" size_t vmmt_generator_workspace_bytes(int M, int V) {
+  return ((size_t)M * V + (size_t)M * 4) * sizeof(float);
+}
+
+extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b,
+                                      const int64_t* target, int64_t pad_idx, int M, int H, int V,
+                                      float* lse, float* stats3, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (workspace_bytes < vmmt_generator_workspace_bytes(M, V)) {
+    vmmt_set_error("generator_nll_fwd: workspace too small");
+    return VMMT_EWORKSPACE;
+  }
+  float* logits = (float*)workspace;
+  float* rowstat = logits + (size_t)M * V;
+  int rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+  if (rc) return rc;
+  row_lse_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, target, pad_idx, lse, rowstat, V);
+  rc = vmmt_check_launch("row_lse");
+  if (rc) return rc;
+  reduce_rowstat_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowstat, M, stats3);
+  return vmmt_check_launch("reduce_rowstat");
+}
+
+extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const float* b,
+                                      const int64_t* target, int64_t pad_idx, const float* lse,
+                                      const float* gscale, float scale, int M, int H, int V, float* dx, float* dW,
+                                      float* db, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  if (workspace_bytes < vmmt_generator_workspace_bytes(M, V)) {
+    vmmt_set_error("generator_nll_bwd: workspace too small");
+    return VMMT_EWORKSPACE;
+  }
+  float* dl = (float*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = vmmt_gemm(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+  if (rc) return rc;
+  dlogits_kernel<<<dim3(ceil_div(V, 256), M), 256, 0, s>>>(dl, lse, target, pad_idx, gscale, scale, V);
+  rc = vmmt_check_launch("dlogits");
+  if (rc) return rc;
+  if (dx) {   // dX[M,H] = dl[M,V] W[V,H]
+    rc = vmmt_gemm(dl, V, 1, W, H, 0, dx, H, M, H, V, nullptr, VMMT_ACT_NONE, 0, stream);
+    if (rc) return rc;
+  }
+  // dW[V,H] += dl^T[V,M] x[M,H]
+  rc = vmmt_gemm(dl, V, 0, x, H, 0, dW, H, V, H, M, nullptr, VMMT_ACT_NONE, 1, stream);
+  if (rc) return rc;
+  return vmmt_colsum_acc(dl, V, M, V, db, stream);
+}
+
+extern "C" int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H,
+                                       int V, float* out, float* lse_ws, void* stream) {
+  int rc = vmmt_gemm(x, H, 1, W, H, 1, out, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+  if (rc) return rc;
+  row_lse_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(out, nullptr, 0, lse_ws, nullptr, V);
+  rc = vmmt_check_launch("row_lse");
+  if (rc) return rc;
+  logprob_kernel<<<dim3(ceil_div(V, 256), M), 256, 0, (cudaStream_t)stream>>>(out, lse_ws, V);
+  return vmmt_check_launch("logprob");
+}

@@ -1,0 +1,61 @@
+"""One contiguous fp32 buffer for all parameters and one for all gradients.
+
+The backward kernels accumulate straight into ``param.grad`` views of the flat gradient buffer, so
+``zero_grad`` is one memset, the data-parallel exchange is one NCCL all-reduce and clip+Adam is two
+launches (see Optim.py).  Parameter identity, names and shapes are untouched, so state_dicts saved
+by the reference load unchanged.
+"""
+import torch
+
+
+def flatten_parameters(module):
+    """Re-point every parameter of ``module`` (and its ``.grad``) into flat buffers.
+    Idempotent; call again after moving the module to another device."""
+    params = []
+    seen = set()
+    for p in module.parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            params.append(p)
+    if not params:
+        return None, None
+    dev = params[0].device
+    sizes = [((p.numel() + 3) // 4) * 4 for p in params]          # keep every tensor 16-byte aligned
+    total = sum(sizes)
+    flat = torch.zeros(total, device=dev, dtype=torch.float32)
+    gflat = torch.zeros(total, device=dev, dtype=torch.float32)
+    off = 0
+    with torch.no_grad():
+        for p, n in zip(params, sizes):
+            view = flat[off: off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = gflat[off: off + p.numel()].view(p.shape)
+            off += n
+    module._flat_params, module._flat_grads = flat, gflat
+    return flat, gflat
+
+
+class FlatParamsMixin:
+    """nn.Module mixin: flat buffers + a zero_grad that keeps the gradient views alive."""
+
+    _flat_params = None
+    _flat_grads = None
+
+    def flatten_parameters(self):
+        return flatten_parameters(self)
+
+    def zero_grad(self, set_to_none=False):
+        if self._flat_grads is not None and not set_to_none:
+            self._flat_grads.zero_()
+            return
+        if self._flat_grads is not None:
+            raise RuntimeError("zero_grad(set_to_none=True) would detach the flat gradient views")
+        return super().zero_grad(set_to_none=set_to_none)
+
+    def _apply(self, fn, *a, **k):
+        had = self._flat_params is not None
+        out = super()._apply(fn, *a, **k)
+        if had:
+            flatten_parameters(self)
+        return out

@@ -1,0 +1,95 @@
+"""Inference / generative networks of VI model 1
+(reference: onmt/modules/NormalVariationalEncoder.py:12-43, 47-110, 113-228, 231-304).
+
+Same classes, constructor arguments, parameter names and return values ``(Normal, h)``.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .Dists import Normal
+
+
+class _Linear(nn.Module):
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        k = 1.0 / in_features ** 0.5
+        self.weight = nn.Parameter(torch.empty(out_features, in_features).uniform_(-k, k))
+        self.bias = nn.Parameter(torch.empty(out_features).uniform_(-k, k))
+
+
+class LocationLayer(nn.Module):
+    """fc2(relu(fc1 x))"""
+
+    def __init__(self, input_size, hidden_size, output_size=None):
+        super().__init__()
+        self.fc1 = _Linear(input_size, hidden_size)
+        self.fc2 = _Linear(hidden_size, output_size if output_size is not None else hidden_size)
+
+    def forward(self, x):
+        h = ops.linear(x, self.fc1.weight, self.fc1.bias, ops.ACT_RELU)
+        return ops.linear(h, self.fc2.weight, self.fc2.bias)
+
+
+class ScaleLayer(nn.Module):
+    """softplus(fc2(relu(fc1 x)))"""
+
+    def __init__(self, input_size, hidden_size, output_size=None):
+        super().__init__()
+        self.fc1 = _Linear(input_size, hidden_size)
+        self.fc2 = _Linear(hidden_size, output_size if output_size is not None else hidden_size)
+
+    def forward(self, x):
+        h = ops.linear(x, self.fc1.weight, self.fc1.bias, ops.ACT_RELU)
+        return ops.linear(h, self.fc2.weight, self.fc2.bias, ops.ACT_SOFTPLUS)
+
+
+class GlobalInferenceNetwork(nn.Module):
+    """Z | x ~ N(loc(h), scale(h)), h = masked mean of the source encodings."""
+
+    def __init__(self, z_dim, input_size, dist_type):
+        assert dist_type == "normal", "only the Normal family is instantiated by the reference configs"
+        super().__init__()
+        self.location = LocationLayer(input_size, z_dim)
+        self.scale = ScaleLayer(input_size, z_dim)
+        self.dist_type = dist_type
+
+    def encode_seq(self, seq, seq_lengths):
+        return ops.MaskedMeanFn.apply(seq, seq_lengths)
+
+    def forward(self, x, x_lengths):
+        h = self.encode_seq(x, x_lengths)
+        return Normal(self.location(h), self.scale(h)), h
+
+
+class GlobalFullInferenceNetwork(GlobalInferenceNetwork):
+    """Z | x, y, v ~ N(loc(h), scale(h)), h = [mean(x); mean(y); v] (global image features)."""
+
+    def __init__(self, z_dim, input_size, dist_type, image_features_type="global"):
+        assert image_features_type in ("global", "posterior"), \
+            "local image features are outside the hot path (SURVEY.md section 2, row 5)"
+        super().__init__(z_dim, input_size, dist_type)
+        self.image_features_type = image_features_type
+
+    def forward(self, x, x_lengths, y, y_lengths, v):
+        hx = self.encode_seq(x, x_lengths)
+        hy = self.encode_seq(y, y_lengths)
+        h = torch.cat([hx, hy, v], -1)
+        return Normal(self.location(h), self.scale(h)), h
+
+
+class ImageGlobalInferenceNetwork(GlobalInferenceNetwork):
+    """V | z ~ N(loc(z * g), scale(z * g)), g = sigmoid(affine(z)); use_source_encodings=False is the
+    only configuration the reference constructs (ModelConstructor.py:536-539)."""
+
+    def __init__(self, latent_dim, image_feats_dim, src_encodings_dim, use_source_encodings, dist_type):
+        assert not use_source_encodings, "use_source_encodings=True is never constructed by the reference"
+        super().__init__(image_feats_dim, latent_dim, dist_type)
+        self.use_source_encodings = use_source_encodings
+        self.gate_affine_transform = _Linear(latent_dim, 1)
+
+    def forward(self, z, x=None, x_lengths=None):
+        gated = ops.GateFn.apply(z, self.gate_affine_transform.weight, self.gate_affine_transform.bias)
+        loc = self.location(gated)
+        # the scale branch never reaches the loss (VILoss.py:321): evaluate it only on demand
+        return Normal(loc, lambda: self.scale(gated.detach()).detach()), None

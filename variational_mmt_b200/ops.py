@@ -1,0 +1,435 @@
+"""torch.autograd.Function wrappers over the libvmmt C ABI.
+
+Every arithmetic step of the hot path runs in libvmmt kernels; torch is used for device memory
+(caching allocator), views and autograd bookkeeping only.  Parameter gradients are ACCUMULATED IN
+PLACE into ``param.grad`` (views of one flat buffer, see ``flat.py``) by the backward kernels
+themselves -- the Functions return ``None`` for parameters -- which is what makes the gradient
+all-reduce and the fused clip+Adam single launches over one contiguous buffer.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, ACT_SOFTPLUS, ACT_SIGMOID, fptr, ptr, stream
+
+_seed_state = {"seed": 0x5EED, "offset": 0}
+
+
+def manual_seed(seed):
+    """Seed of the in-kernel Philox streams (dropout masks, latent noise)."""
+    _seed_state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _seed_state["offset"] = 0
+
+
+def _next_offset():
+    _seed_state["offset"] += 1
+    return _seed_state["offset"]
+
+
+def grad_buf(p):
+    """The tensor parameter gradients are accumulated into (allocated zero-filled on first use)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def gemm(a, b, out, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, accumulate=0):
+    """out[M,N] = act(op(a) op(b) + bias) (+out).  a, b, out: 2-D views with unit inner stride."""
+    assert a.stride(-1) == 1 and b.stride(-1) == 1 and out.stride(-1) == 1
+    L.call("vmmt_gemm", fptr(a), a.stride(0), int(a_kmajor), fptr(b), b.stride(0), int(b_kmajor),
+           fptr(out), out.stride(0), M, N, K, fptr(bias), act, int(accumulate), stream())
+    return out
+
+
+def colsum_acc(a, M, N, out):
+    L.call("vmmt_colsum_acc", fptr(a), a.stride(0), M, N, fptr(out), stream())
+
+
+# --------------------------------------------------------------------------------------------
+class EmbeddingFn(Function):
+    """nn.Embedding lookup (onmt/modules/Embeddings.py:169-188)."""
+
+    @staticmethod
+    def forward(ctx, idx, weight, pad_idx):
+        idx = idx.contiguous()
+        n, E = idx.numel(), weight.shape[1]
+        out = torch.empty(*idx.shape, E, device=weight.device, dtype=torch.float32)
+        L.call("vmmt_embedding_fwd", ptr(idx), n, fptr(weight), E, fptr(out), stream())
+        ctx.save_for_backward(idx)
+        ctx.weight, ctx.pad_idx = weight, pad_idx
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        w = ctx.weight
+        dout = dout.contiguous()
+        L.call("vmmt_embedding_bwd", ptr(idx), idx.numel(), fptr(dout), w.shape[1], ctx.pad_idx,
+               fptr(grad_buf(w)), stream())
+        return None, None, None
+
+
+class LinearFn(Function):
+    """y = act(x W[:, c0:c1]^T + b), optionally y = act(x W^T + b + addend) (nn.Linear + activation)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, cols, addend):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < x2.shape[1]):
+            x2 = x2.contiguous()
+        c0, c1 = cols if cols is not None else (0, weight.shape[1])
+        wv = weight[:, c0:c1]
+        M, K, N = x2.shape[0], c1 - c0, weight.shape[0]
+        if addend is not None:
+            y = addend.reshape(M, N).clone()
+            gemm(x2, wv, y, M, N, K, bias=bias, act=act, accumulate=2)
+        else:
+            y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+            gemm(x2, wv, y, M, N, K, bias=bias, act=act)
+        ctx.save_for_backward(x2, y)
+        ctx.weight, ctx.bias, ctx.act, ctx.cols, ctx.xshape = weight, bias, act, (c0, c1), x.shape
+        ctx.has_addend = addend is not None
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, y = ctx.saved_tensors
+        weight, bias, act = ctx.weight, ctx.bias, ctx.act
+        c0, c1 = ctx.cols
+        M, K, N = x2.shape[0], c1 - c0, weight.shape[0]
+        dy = dy.reshape(M, N).contiguous()
+        if act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            L.call("vmmt_act_bwd", fptr(dy), fptr(y), fptr(dpre), dy.numel(), act, stream())
+        else:
+            dpre = dy
+        if weight.requires_grad:
+            gw = grad_buf(weight)[:, c0:c1]
+            gemm(dpre, x2, gw, N, K, M, a_kmajor=False, b_kmajor=False, accumulate=1)   # dW += dpre^T x
+        if bias is not None and bias.requires_grad:
+            colsum_acc(dpre, M, N, grad_buf(bias))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+            gemm(dpre, weight[:, c0:c1], dx, M, K, N, b_kmajor=False)                    # dx = dpre W
+            dx = dx.view(ctx.xshape)
+        dadd = dpre.view(*ctx.xshape[:-1], N) if ctx.has_addend and ctx.needs_input_grad[5] else None
+        return dx, None, None, None, None, dadd
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, cols=None, addend=None):
+    return LinearFn.apply(x, weight, bias, act, cols, addend)
+
+
+# --------------------------------------------------------------------------------------------
+class LSTMLayerFn(Function):
+    """One nn.LSTM layer, one or two directions (onmt/Models.py:124-149,892-893; VI_Model1.py:106).
+
+    forward(x [T,N,In], h0, c0 [ndir,N,Hd] | None, rowbias [N,4H] | None, lengths | None, cfg,
+            *weights)  with weights = (w_ih, w_hh, b_ih, b_hh) per direction and
+    cfg = dict(in_cols=(c0,c1) | None, save=bool)  ->  out [T,N,ndir*Hd], hT, cT [ndir,N,Hd]
+    """
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, rowbias, lengths, cfg, *weights):
+        ndir = len(weights) // 4
+        T, N, In = x.shape
+        Hd = weights[1].shape[1]
+        dev = x.device
+        x = x.contiguous()
+        save = cfg.get("save", True)
+        c0c, c1c = cfg.get("in_cols") or (0, weights[0].shape[1])
+        assert c1c - c0c == In
+        gx = torch.empty(ndir, T, N, 4 * Hd, device=dev, dtype=torch.float32)
+        out = torch.empty(T, N, ndir * Hd, device=dev, dtype=torch.float32)
+        hT = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32)
+        cT = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32)
+        gates = torch.empty(ndir, T, N, 4 * Hd, device=dev, dtype=torch.float32) if save else None
+        cs = torch.empty(ndir, T, N, Hd, device=dev, dtype=torch.float32) if save else None
+        if h0 is not None:
+            h0, c0 = h0.contiguous(), c0.contiguous()
+        if rowbias is not None:
+            rowbias = rowbias.contiguous()
+        dirs = (L.LstmDir * ndir)()
+        x2 = x.view(T * N, In)
+        for d in range(ndir):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
+            gemm(x2, w_ih[:, c0c:c1c], gx[d].view(T * N, 4 * Hd), T * N, 4 * Hd, In)
+            D = dirs[d]
+            D.gx, D.w_hh, D.b_ih, D.b_hh = fptr(gx[d]), fptr(w_hh), fptr(b_ih), fptr(b_hh)
+            D.rowbias = fptr(rowbias)
+            D.h0 = fptr(h0[d]) if h0 is not None else None
+            D.c0 = fptr(c0[d]) if c0 is not None else None
+            D.out = out.data_ptr() + 4 * d * Hd
+            D.out_ld = ndir * Hd
+            D.hT, D.cT = fptr(hT[d]), fptr(cT[d])
+            D.gates = fptr(gates[d]) if save else None
+            D.cs = fptr(cs[d]) if save else None
+            D.reverse = 1 if d == 1 else 0
+        ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
+        ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
+        L.call("vmmt_lstm_seq_fwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
+        if save:
+            ctx.save_for_backward(x, out, gates, cs, h0, c0, rowbias, lengths)
+            ctx.weights, ctx.cfg = weights, (ndir, T, N, In, Hd, c0c, c1c)
+        ctx.set_materialize_grads(False)
+        return out, hT, cT
+
+    @staticmethod
+    def backward(ctx, dout, dhT, dcT):
+        x, out, gates, cs, h0, c0, rowbias, lengths = ctx.saved_tensors
+        weights = ctx.weights
+        ndir, T, N, In, Hd, c0c, c1c = ctx.cfg
+        dev = x.device
+        dout = dout.contiguous() if dout is not None else None
+        dhT = dhT.contiguous() if dhT is not None else None
+        dcT = dcT.contiguous() if dcT is not None else None
+        dg = torch.empty(ndir, T, N, 4 * Hd, device=dev, dtype=torch.float32)
+        need_h0 = h0 is not None and ctx.needs_input_grad[1]
+        dh0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
+        dc0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
+        dirs = (L.LstmDirBwd * ndir)()
+        for d in range(ndir):
+            D = dirs[d]
+            D.w_hh, D.gates, D.cs = fptr(weights[4 * d + 1]), fptr(gates[d]), fptr(cs[d])
+            D.c0 = fptr(c0[d]) if c0 is not None else None
+            D.dout = (dout.data_ptr() + 4 * d * Hd) if dout is not None else None
+            D.dout_ld = ndir * Hd
+            D.dhT = fptr(dhT[d]) if dhT is not None else None
+            D.dcT = fptr(dcT[d]) if dcT is not None else None
+            D.dgates = fptr(dg[d])
+            D.dh0 = fptr(dh0[d]) if need_h0 else None
+            D.dc0 = fptr(dc0[d]) if need_h0 else None
+            D.reverse = 1 if d == 1 else 0
+        L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, stream())
+        x2 = x.view(T * N, In)
+        dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        drow = None
+        for d in range(ndir):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
+            dg2 = dg[d].view(T * N, 4 * Hd)
+            if dx is not None:                                         # dx (+)= dG W_ih
+                gemm(dg2, w_ih[:, c0c:c1c], dx, T * N, In, 4 * Hd, b_kmajor=False, accumulate=int(d > 0))
+            if w_ih.requires_grad:                                     # dW_ih += dG^T x
+                gemm(dg2, x2, grad_buf(w_ih)[:, c0c:c1c], 4 * Hd, In, T * N, a_kmajor=False,
+                     b_kmajor=False, accumulate=1)
+            if w_hh.requires_grad and T > 1:                           # dW_hh += dG[t]^T h[t -/+ 1]
+                o_d = out[:, :, d * Hd:(d + 1) * Hd]
+                if d == 0:
+                    a_, b_ = dg[d][1:], o_d[:-1]
+                else:
+                    a_, b_ = dg[d][:-1], o_d[1:]
+                # rows (t,n) of the shifted views are contiguous blocks with row strides 4Hd / ndir*Hd
+                gemm(a_.reshape(-1, 4 * Hd), b_.reshape((T - 1) * N, Hd) if ndir == 1 else _rows(b_),
+                     grad_buf(w_hh), 4 * Hd, Hd, (T - 1) * N, a_kmajor=False, b_kmajor=False, accumulate=1)
+            if w_hh.requires_grad and h0 is not None:                  # first step uses h0
+                t0 = 0 if d == 0 else T - 1
+                gemm(dg[d][t0], h0[d], grad_buf(w_hh), 4 * Hd, Hd, N, a_kmajor=False, b_kmajor=False,
+                     accumulate=1)
+            if b_ih.requires_grad:
+                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih))
+            if b_hh.requires_grad:
+                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_hh))
+        if rowbias is not None and ctx.needs_input_grad[3]:
+            drow = torch.zeros(N, 4 * Hd, device=dev, dtype=torch.float32)
+            colsum_acc(dg[0].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
+        if dx is not None:
+            dx = dx.view(T, N, In)
+        return (dx, dh0, dc0, drow, None, None) + (None,) * len(weights)
+
+
+def _rows(v):
+    """[T,N,Hd] slice of a [T,N,ndir*Hd] buffer viewed as (T*N) rows with the parent's row stride."""
+    T, N, Hd = v.shape
+    return v.as_strided((T * N, Hd), (v.stride(1), 1), v.storage_offset())
+
+
+class AttentionCoreFn(Function):
+    """scores + masked softmax + context (onmt/modules/GlobalAttention.py:108-113,169-184)."""
+
+    @staticmethod
+    def forward(ctx, qp, context, lengths):
+        qp, context = qp.contiguous(), context.contiguous()
+        T, B, H = qp.shape
+        S = context.shape[0]
+        align = torch.empty(T, B, S, device=qp.device, dtype=torch.float32)
+        cvec = torch.empty(T, B, H, device=qp.device, dtype=torch.float32)
+        L.call("vmmt_attention_fwd", fptr(qp), fptr(context), ptr(lengths), fptr(align), fptr(cvec),
+               T, B, S, H, stream())
+        ctx.save_for_backward(qp, context, align, lengths)
+        ctx.mark_non_differentiable(align)
+        return cvec, align
+
+    @staticmethod
+    def backward(ctx, dcvec, _dalign):
+        qp, context, align, lengths = ctx.saved_tensors
+        T, B, H = qp.shape
+        S = context.shape[0]
+        dcvec = dcvec.contiguous()
+        ds = torch.empty(T, B, S, device=qp.device, dtype=torch.float32)
+        dqp = torch.empty_like(qp)
+        dctx = torch.empty_like(context)
+        L.call("vmmt_attention_bwd", fptr(dcvec), fptr(qp), fptr(context), fptr(align), ptr(lengths),
+               fptr(ds), fptr(dqp), fptr(dctx), 0, T, B, S, H, stream())
+        return dqp, dctx, None
+
+
+class MaskedMeanFn(Function):
+    """GlobalInferenceNetwork.encode_seq (onmt/modules/NormalVariationalEncoder.py:65-84)."""
+
+    @staticmethod
+    def forward(ctx, x, lengths):
+        x = x.contiguous()
+        T, B, H = x.shape
+        out = torch.empty(B, H, device=x.device, dtype=torch.float32)
+        L.call("vmmt_masked_mean_fwd", fptr(x), ptr(lengths), fptr(out), H, T, B, H, stream())
+        ctx.save_for_backward(lengths)
+        ctx.dims = (T, B, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (lengths,) = ctx.saved_tensors
+        T, B, H = ctx.dims
+        dout = dout.contiguous()
+        dx = torch.empty(T, B, H, device=dout.device, dtype=torch.float32)
+        L.call("vmmt_masked_mean_bwd", fptr(dout), H, ptr(lengths), fptr(dx), 0, T, B, H, stream())
+        return dx, None
+
+
+class DropoutFn(Function):
+    """Inverted dropout with an in-kernel Philox mask, regenerated (not stored) in backward."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        ctx.p, ctx.seed, ctx.offset = p, _seed_state["seed"], _next_offset()
+        L.call("vmmt_dropout", fptr(x), fptr(y), x.numel(), p, ctx.seed, ctx.offset, stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        L.call("vmmt_dropout", fptr(dy), fptr(dx), dy.numel(), ctx.p, ctx.seed, ctx.offset, stream())
+        return dx, None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return DropoutFn.apply(x, float(p))
+
+
+def normal_sample(mu, sd, eps=None):
+    """z = mu + sd*eps without a pathwise gradient (torch.normal semantics, onmt/modules/Dists.py:21-26)."""
+    with torch.no_grad():
+        mu_c, sd_c = mu.detach().contiguous(), sd.detach().contiguous()
+        z = torch.empty_like(mu_c)
+        L.call("vmmt_normal_sample", fptr(mu_c), fptr(sd_c), fptr(eps.contiguous()) if eps is not None else None,
+               fptr(z), z.numel(), _seed_state["seed"], _next_offset(), stream())
+    return z
+
+
+class GateFn(Function):
+    """gated = z * sigmoid(z.w + b); z carries no gradient (hazard H2)
+    (onmt/modules/NormalVariationalEncoder.py:286-299)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, bias):
+        z = z.contiguous()
+        B, Z = z.shape
+        gate = torch.empty(B, device=z.device, dtype=torch.float32)
+        gated = torch.empty_like(z)
+        L.call("vmmt_gate_fwd", fptr(z), fptr(weight), fptr(bias), fptr(gate), fptr(gated), B, Z, stream())
+        ctx.save_for_backward(z, gate)
+        ctx.weight, ctx.bias = weight, bias
+        return gated
+
+    @staticmethod
+    def backward(ctx, dgated):
+        z, gate = ctx.saved_tensors
+        B, Z = z.shape
+        dgated = dgated.contiguous()
+        dpre = torch.empty(B, device=z.device, dtype=torch.float32)
+        L.call("vmmt_gate_bwd", fptr(dgated), fptr(z), fptr(gate), fptr(dpre), fptr(grad_buf(ctx.weight)),
+               fptr(grad_buf(ctx.bias)), B, Z, stream())
+        return None, None, None
+
+
+class VILossFn(Function):
+    """NLL + image log-prob + KL in one node (onmt/VILoss.py:217-513).
+
+    forward(out2d [M,H], target [M], gen_w, gen_b, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, cfg) ->
+      loss [1] = NLL - IMG + kl_weight*KL,  stats [8] = {nll, n_words, n_correct, kl, img_logprob,
+      img_cos, 0, 0}.  cfg: pad_idx, kl_weight, legacy_image_grad.
+    """
+
+    @staticmethod
+    def forward(ctx, out2d, target, gen_w, gen_b, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, cfg):
+        dev = out2d.device
+        out2d = out2d.contiguous()
+        target = target.contiguous()
+        M, H = out2d.shape
+        V = gen_w.shape[0]
+        stats = torch.zeros(8, device=dev, dtype=torch.float32)
+        lse = torch.empty(M, device=dev, dtype=torch.float32)
+        wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
+        ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
+        L.call("vmmt_generator_nll_fwd", fptr(out2d), fptr(gen_w), fptr(gen_b), ptr(target), cfg["pad_idx"],
+               M, H, V, fptr(lse), fptr(stats[0:3]), fptr(ws), wsb, stream())
+        mu_q, sd_q = mu_q.contiguous(), sd_q.contiguous()
+        B, Z = mu_q.shape
+        if mu_p is not None:
+            mu_p, sd_p = mu_p.contiguous(), sd_p.contiguous()
+        L.call("vmmt_kl_fwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(stats[3:4]), B, Z, stream())
+        img_loc, img_v = img_loc.contiguous(), img_v.contiguous()
+        D = img_loc.shape[1]
+        rowstats = torch.empty(B, 4, device=dev, dtype=torch.float32)
+        L.call("vmmt_image_loss_fwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(stats[4:6]), B, D, stream())
+        kw = float(cfg["kl_weight"])
+        loss = (stats[0] - stats[4] + kw * stats[3]).reshape(1)
+        ctx.save_for_backward(out2d, target, lse, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, rowstats)
+        ctx.gen_w, ctx.gen_b, ctx.cfg = gen_w, gen_b, cfg
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, dloss, _dstats):
+        out2d, target, lse, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, rowstats = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = out2d.device
+        M, H = out2d.shape
+        V = ctx.gen_w.shape[0]
+        gs = dloss.reshape(1).contiguous()                     # device scalar: no host sync
+        dx = torch.empty(M, H, device=dev, dtype=torch.float32)
+        wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
+        ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
+        L.call("vmmt_generator_nll_bwd", fptr(out2d), fptr(ctx.gen_w), fptr(ctx.gen_b), ptr(target),
+               cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), fptr(grad_buf(ctx.gen_w)),
+               fptr(grad_buf(ctx.gen_b)), fptr(ws), wsb, stream())
+        B, Z = mu_q.shape
+        dmq, dsq = torch.empty_like(mu_q), torch.empty_like(sd_q)
+        dmp = torch.empty_like(mu_q) if mu_p is not None else None
+        dsp = torch.empty_like(mu_q) if mu_p is not None else None
+        L.call("vmmt_kl_bwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(dmq), fptr(dsq), fptr(dmp),
+               fptr(dsp), fptr(gs), float(cfg["kl_weight"]), B, Z, stream())
+        D = img_loc.shape[1]
+        dloc = torch.empty_like(img_loc)
+        L.call("vmmt_image_loss_bwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(dloc), fptr(gs), 1.0,
+               int(cfg.get("legacy_image_grad", True)), B, D, stream())
+        return dx, None, None, None, dmq, dsq, dmp, dsp, dloc, None, None
+
+
+def generator_logprobs(x2d, weight, bias):
+    """log_softmax(x W^T + b) materialised [M,V] (decode: onmt/translate/TranslatorMultimodalVI.py:199)."""
+    x2d = x2d.contiguous()
+    M, H = x2d.shape
+    V = weight.shape[0]
+    out = torch.empty(M, V, device=x2d.device, dtype=torch.float32)
+    lse = torch.empty(M, device=x2d.device, dtype=torch.float32)
+    L.call("vmmt_generator_logprobs", fptr(x2d), fptr(weight), fptr(bias), M, H, V, fptr(out), fptr(lse), stream())
+    return out
