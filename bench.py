@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- training target-tokens/s of the VI-model-1 step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg1|cfg1_ragged|cfg5|decode] [--dtype fp32] [--profile-calls]
+
+One "step" = one optimiser update of the conditional VI model 1 on one synthetic Multi30k-shaped
+batch per rank: NMTVIModel.forward -> NMTVIModel1LossCompute.
+sharded_compute_loss (generator + NLL + image loss + KL, forward and backward) -> [NCCL sum
+all-reduce of the flat gradient buffer when N > 1] -> global-norm clip + Adam.  Dropout 0.5 and the
+in-kernel Philox latent noise are ON (training configuration of run_translated_m30k_only.sh).
+
+  value : whole-job tokens/s with the batch already resident in HBM (device-timed, CUDA events on the
+          launching stream, max over ranks).
+  e2e   : same metric through the public module API with HOST (pinned) buffers: every step copies
+          that step's ids / lengths / image features host->device and reads the loss statistics
+          device->host inside the timed region.
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+
+`--impl reference` times the CPU path (the oracle port of the reference step -- the reference itself
+is a Python package that lives in /root/reference and does not travel to the GPU box) on the host
+cores with every thread torch can use; rank 0 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+WORKLOADS = {
+    # name: (model kwargs, batch kwargs, description)
+    "cfg1": (dict(v=10000, emb=500, hidden=500, z=500, conditional=True),
+             dict(batch_size=40, full_length=(30, 30)),
+             "translated-Multi30k training shape: conditional VI-model-1, B=40/GPU, S=30, tgt_len=32, "
+             "E=H=Z=500, 2 layers, D=2048, V=10000, dropout 0.5"),
+    "cfg1_ragged": (dict(v=10000, emb=500, hidden=500, z=500, conditional=True),
+                    dict(batch_size=40, full_length=None),
+                    "as cfg1 with lengths ~ clip(round(N(14,5)),3,50)"),
+    "cfg5": (dict(v=32000, emb=1024, hidden=1024, z=1024, conditional=True),
+             dict(batch_size=512, full_length=(80, 78)),
+             "scaled stress: H=E=Z=1024, V=32000, B=512/GPU, 80-token sequences"),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:                                     # noqa: BLE001
+            self.ok = False
+
+    _NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+              0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting",
+              0x100: "display_clock_setting", 0x10: "sync_boost"}
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:                                 # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _gpu_index_for_nvml(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:                                     # noqa: BLE001
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference training step on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import cpu_baseline
+    mk, bk, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    res = cpu_baseline.time_train_steps(mk, bk, steps=args.steps, warmup=args.warmup, threads=cores,
+                                        budget_s=args.cpu_budget)
+    line = {
+        "impl": "reference", "metric": "train_target_tokens_per_sec", "value": res["tokens_per_s"],
+        "unit": "tokens/s", "n_gpus": args.gpus, "steps": res["steps"], "warmup": res["warmup"],
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": desc, "global_batch": bk["batch_size"],
+                   "tokens_per_step": res["tokens_per_step"]},
+        "cpu_baseline": {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"],
+                         "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": res["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    n_gpus = world
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import synthetic, _lib
+
+    mk, bk, desc = WORKLOADS[args.workload]
+    B = bk["batch_size"]
+    opt = synthetic.make_opt(emb=mk["emb"], hidden=mk["hidden"], z_dim=mk["z"], conditional=mk["conditional"],
+                             dropout=0.5)
+    fields = synthetic.make_fields(mk["v"], mk["v"])
+    torch.manual_seed(3435)
+    model = vm.make_vi_model_mmt(opt, fields, gpu=True)
+    model.train()
+    vm.manual_seed(3435 + rank)
+    loss_fn = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+    optim = vm.Optim("adam", 0.002, 5)
+    optim.set_parameters(model.parameters())
+    n_params = sum(p.numel() for p in model.parameters())
+
+    # a ring of different host batches (pinned), one per step modulo NB
+    NB = 8
+    host = [synthetic.random_batch(mk["v"], mk["v"], B, 2048, seed=1000 * rank + i, pinned=True,
+                                   full_length=bk.get("full_length")) for i in range(NB)]
+    tokens = [int((h[2][1:] != synthetic.PAD).sum()) for h in host]
+    # the reference trainer scores only the first 32 decoder positions (hazard H4); count what it counts
+    shard = 32 if args.workload != "cfg5" else 128
+    tokens = [int((h[2][1:1 + shard] != synthetic.PAD).sum()) for h in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    norm = B * n_gpus                                     # divide by the GLOBAL sentence count
+
+    class Bt:
+        pass
+
+    def to_dev(h):
+        return [t.to(dev, non_blocking=True) for t in h]
+
+    def step(d, read_stats):
+        src, sl, tgt, tl, img = d
+        model.zero_grad()
+        out, attns, _ = model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
+        b = Bt()
+        b.tgt, b.batch_size = tgt, B
+        st = loss_fn.sharded_compute_loss(b, out, attns, 0, tgt.size(0), shard, norm)
+        optim.step()
+        if read_stats:
+            return st._vec.cpu()                           # device->host read of the step's statistics
+        return st._vec
+
+    resident = [to_dev(h) for h in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        tok = 0
+        for i in range(nsteps):
+            if e2e:
+                step(to_dev(host[i % NB]), True)
+            else:
+                step(resident[i % NB], False)
+            tok += tokens[i % NB]
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms, wall * 1e3, float(tok)], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            return float(mx[0]), float(mx[1]), float(sm[2])
+        return float(t[0]), float(t[1]), float(t[2])
+
+    # warm-up (also sizes the caching allocator)
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % NB], False)
+    barrier()
+
+    sampler = ClockSampler(_gpu_index_for_nvml(local_rank))
+    sampler.start()
+    l0 = _lib.lib.vmmt_launch_count()
+    dev_ms, wall_ms, tok = timed(args.steps, e2e=False)
+    launches = _lib.lib.vmmt_launch_count() - l0
+    for i in range(2):
+        step(to_dev(host[i % NB]), True)
+    e2e_ms, e2e_wall, e2e_tok = timed(args.steps, e2e=True)
+    clocks = sampler.stop()
+    # host-side wall clock bounds the device time from above when the host is the bottleneck
+    value = tok / (max(dev_ms, 1e-9) / 1e3)
+    e2e_value = e2e_tok / (max(e2e_wall, e2e_ms) / 1e3)
+
+    # ---- per-call device time of the C-ABI entry points (one extra, untimed step)
+    prof = []
+    _lib.set_profile(prof)
+    step(resident[0], False)
+    torch.cuda.synchronize()
+    _lib.set_profile(None)
+    per_call = {}
+    for name, _a, e0, e1 in prof:
+        per_call.setdefault(name, [0, 0.0])
+        per_call[name][0] += 1
+        per_call[name][1] += e0.elapsed_time(e1)
+    top = sorted(per_call.items(), key=lambda kv: -kv[1][1])
+
+    roof = None
+    cpu_b = None
+    if rank == 0:
+        peaks, how = _peaks()
+        roof = roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev)
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_baseline
+            cores = os.cpu_count() or 1
+            r = cpu_baseline.time_train_steps(mk, bk, steps=2, warmup=1, threads=cores, budget_s=args.cpu_budget)
+            cpu_b = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "port",
+                     "sample": r["sample"]}
+        line = {
+            "metric": "train_target_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": desc, "global_batch": B * n_gpus,
+                       "tokens_per_step": tok / args.steps, "params": n_params,
+                       "gemm": "tf32 tcgen05 (fp32 storage, fp32 accumulate)" if _lib.lib.vmmt_get_gemm_mode() == 0
+                               else "fp32 simt",
+                       "parallelism": "dp%d" % n_gpus,
+                       "l2": "no flush: each step streams params+grads+Adam moments (%.0f MB) > 126 MB L2 and "
+                             "rotates over %d different batches" % (16.0 * n_params / 1e6, NB)},
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 32, "ms_per_step": max(e2e_wall, e2e_ms) / args.steps},
+            "host_wall_ms_per_step": wall_ms / args.steps,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu_b,
+            "top_calls_ms": {k: round(v[1], 3) for k, v in top[:8]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
+    """Times the dominant kernel of the step (the fused generator+NLL forward GEMM) in isolation with
+    CUDA events on the launching stream and reports it against the measured tensor peak.  DESIGN.md
+    ("Measurement") states the algorithmic FLOPs."""
+    import torch
+    from variational_mmt_b200.ops import fptr, ptr, stream
+    H, V, B = mk["hidden"], mk["v"], bk["batch_size"]
+    T = min(shard, (bk["full_length"][1] + 1) if bk.get("full_length") else 31)
+    M = T * B
+    x = torch.randn(M, H, device=dev) * 0.5
+    tgt = torch.randint(4, V, (M,), device=dev)
+    W, b = model.generator[0].weight, model.generator[0].bias
+    lse = torch.empty(M, device=dev)
+    stats = torch.zeros(3, device=dev)
+    wsb = _lib.lib.vmmt_generator_workspace_bytes(M, V)
+    ws = torch.empty(wsb // 4, device=dev)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)           # 256 MB > L2
+
+    def run():
+        _lib.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), 1, M, H, V, fptr(lse),
+                  fptr(stats), fptr(ws), wsb, stream())
+    for _ in range(3):
+        run()
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    flops = 2.0 * M * H * V
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops"] / 2.0        # TF32 runs at half the bf16 tensor rate
+    return {"kernel": "vmmt_generator_nll_fwd (M=%d,H=%d,V=%d)" % (M, H, V), "bound": "tensor",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "ms": ms,
+            "peak_source": "%s bf16 burst %.0f TF/s / 2 (tf32 operands)" % (how, peaks["bf16_tflops"])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

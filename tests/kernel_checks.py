@@ -87,7 +87,7 @@ def check_lstm(tol=2e-5):
              ("tiny-odd", 7, 5, 33, 50, True, True, False),
              ("tgtenc-bi", 40, 32, 500, 250, False, False, False)]
     for name, T, N, In, H, masked, with_h0, with_rb in cases:
-        ndir = 2 if "bi" in name else 1
+        ndir = 2 if name.endswith("-bi") else 1
         x = _r(T, N, In, scale=0.5, seed=11).requires_grad_(True)
         ws = []
         for d in range(ndir):

@@ -234,7 +234,8 @@ class LSTMLayerFn(Function):
                 colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_hh))
         if rowbias is not None and ctx.needs_input_grad[3]:
             drow = torch.zeros(N, 4 * Hd, device=dev, dtype=torch.float32)
-            colsum_acc(dg[0].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
+            for d in range(ndir):                                      # the term enters every direction
+                colsum_acc(dg[d].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
         if dx is not None:
             dx = dx.view(T, N, In)
         return (dx, dh0, dc0, drow, None, None) + (None,) * len(weights)
