@@ -48,7 +48,7 @@ def relerr(a, b):
 
 
 def maxabs(a, b):
-    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+    return float(np.abs(np.asarray(a, np.float64).reshape(-1) - np.asarray(b, np.float64).reshape(-1)).max())
 
 
 def named_grads(model):

@@ -104,3 +104,30 @@ def test_synth_is_deterministic():
     assert synth.num_params(synth.CFG1) == 42781301
     w = p["generator.0.bias"]
     assert w.shape == (150,) and np.abs(w).max() <= 0.1
+
+
+def test_cpu_baseline_fast_path_equals_restatement():
+    """oracle/cpu_baseline.py (nn.LSTM + pack_padded_sequence, what bench.py times as the CPU arm)
+    gives the same losses and gradients as the explicit-loop restatement."""
+    import torch
+    from oracle import cpu_baseline as cb
+    for cfg in (synth.TINY, synth.TINY_FIXED):
+        params = synth.make_params(cfg, 3435, 0.1)
+        batch = synth.make_batch(cfg, batch_size=6, seed=2, t_force=20)
+        m = cb.CpuStep(cfg, params, dropout=0.0)
+        m.train()
+        loss, stats, _ = m.forward_loss(R.to_torch_batch(batch), training=True)
+        loss.backward()
+        grads, ostats, _ = R.train_step_grads(params, cfg, batch)
+        for k in ("nmt", "td_kl_before", "img_feats_loss", "elbo"):
+            assert stats[k] == pytest.approx(ostats[k], rel=1e-5), k
+        assert stats["n_words"] == ostats["n_words"]
+        for k, kk in m._names.items():
+            g = m.p[kk].grad
+            if grads[k] is None:
+                assert g is None or not bool(g.any()), k
+                continue
+            if "emb_luts" in k:
+                g = g.clone()
+                g[1] = 0
+            assert float((g - grads[k]).norm() / grads[k].norm().clamp_min(1e-30)) < 1e-4, k

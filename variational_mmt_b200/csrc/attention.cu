@@ -147,16 +147,17 @@ attn_bwd_query_kernel(const float* __restrict__ dc, const float* __restrict__ ct
       if (j < S) dscore[q * S + j] = ds[r];
     }
     float* out = dqp + q * H;
-    for (int k = lane; k < H; k += 32) {
+    for (int k0 = 0; k0 < H; k0 += 32) {          // all lanes stay in the loop: shuffles need the full warp
+      const int k = k0 + lane;
       float acc = 0.f;
       for (int j = 0; j < len; ++j) {
         float v = 0.f;
 #pragma unroll
         for (int r = 0; r < SMAX / 32; ++r) if (r == (j >> 5)) v = ds[r];
         v = __shfl_sync(0xffffffffu, v, j & 31);
-        acc = fmaf(v, ctx[((size_t)j * B + b) * H + k], acc);
+        if (k < H) acc = fmaf(v, ctx[((size_t)j * B + b) * H + k], acc);
       }
-      out[k] = acc;
+      if (k < H) out[k] = acc;
     }
   }
 }
