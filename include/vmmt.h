@@ -88,7 +88,7 @@ int vmmt_lstm_seq_supported(int ndir, int N, int H);
 int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
                       void* workspace, size_t workspace_bytes, void* stream);
 int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
-                      void* stream);
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* single-step cell on pre-summed gate pre-activations (decode with large sentences x beam). */
 int vmmt_lstm_cell_fwd(const float* gates_pre, const float* b_ih, const float* b_hh, const float* rowbias,
                        const float* c_prev, float* h_out, float* c_out, int N, int H, void* stream);

@@ -48,7 +48,7 @@ SIGNATURES = {
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_lstm_seq_supported": (I, [I, I, I]),
     "vmmt_lstm_seq_fwd": (I, [C.POINTER(LstmDir), I, P, I, I, I, P, SZ, P]),
-    "vmmt_lstm_seq_bwd": (I, [C.POINTER(LstmDirBwd), I, P, I, I, I, P]),
+    "vmmt_lstm_seq_bwd": (I, [C.POINTER(LstmDirBwd), I, P, I, I, I, P, SZ, P]),
     "vmmt_lstm_cell_fwd": (I, [P, P, P, P, P, P, P, I, I, P]),
     "vmmt_attention_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "vmmt_attention_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P]),

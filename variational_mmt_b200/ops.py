@@ -203,7 +203,9 @@ class LSTMLayerFn(Function):
             D.dh0 = fptr(dh0[d]) if need_h0 else None
             D.dc0 = fptr(dc0[d]) if need_h0 else None
             D.reverse = 1 if d == 1 else 0
-        L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, stream())
+        ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
+        ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
+        L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
         x2 = x.view(T * N, In)
         dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         drow = None
