@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "vmmt_internal.h"
+#include "lstm_tc.h"
 
 namespace {
 
@@ -372,12 +373,25 @@ int make_plan(bool bwd, int ndir, int N, int H, Plan* best) {
 
 template <typename K>
 int resident_launch(K kernel, int grid, size_t smem, void* params, cudaStream_t s, const char* what) {
-  VMMT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  VMMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LSTM_THREADS, smem));
-  if (per_sm * vmmt_num_sms() < grid) {
-    vmmt_set_error("%s: grid of %d CTAs is not co-resident (%d/SM)", what, grid, per_sm);
-    return VMMT_ELAUNCH;
+  // attributes / occupancy are checked once per (kernel, device, configuration), not per launch
+  static size_t smem_set[64] = {0};
+  static int ok_grid[64] = {0};
+  static size_t ok_smem[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem > smem_set[dev]) {
+    VMMT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[dev] = smem;
+  }
+  if (!(grid <= ok_grid[dev] && smem <= ok_smem[dev])) {
+    int per_sm = 0;
+    VMMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LSTM_THREADS, smem));
+    if (per_sm * vmmt_num_sms() < grid) {
+      vmmt_set_error("%s: grid of %d CTAs is not co-resident (%d/SM)", what, grid, per_sm);
+      return VMMT_ELAUNCH;
+    }
+    ok_grid[dev] = grid; ok_smem[dev] = smem;
   }
   // cooperative launch = the driver guarantees co-residency of the whole grid (the inter-CTA
   // barriers above spin); it is stream-ordered and graph-capturable like any other launch
@@ -405,6 +419,9 @@ extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_
                                  void* stream) {
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_fwd: ndir must be 1 or 2 (got %d)", ndir);
   VMMT_REQUIRE(T > 0 && N > 0 && H > 0, "lstm_seq_fwd: bad dims T=%d N=%d H=%d", T, N, H);
+  // tensor-core cluster path (default); VMMT_GEMM=simt / vmmt_set_gemm_mode(1) selects the exact-fp32 SIMT kernels
+  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && vmmt_lstm_tc_supported(ndir, N, H))
+    return vmmt_lstm_tc_fwd(dirs, ndir, lengths, T, N, H, (cudaStream_t)stream);
   Plan p;
   VMMT_REQUIRE(make_plan(false, ndir, N, H, &p) == VMMT_OK,
                "lstm_seq_fwd: N=%d H=%d does not fit the persistent kernel", N, H);
@@ -431,6 +448,9 @@ extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_
 extern "C" int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths,
                                  int T, int N, int H, void* workspace, size_t workspace_bytes, void* stream) {
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_bwd: ndir must be 1 or 2 (got %d)", ndir);
+  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_SIMT_BWD") &&
+      vmmt_lstm_tc_supported(ndir, N, H))
+    return vmmt_lstm_tc_bwd(dirs, ndir, lengths, T, N, H, (cudaStream_t)stream);
   Plan p;
   VMMT_REQUIRE(make_plan(true, ndir, N, H, &p) == VMMT_OK,
                "lstm_seq_bwd: N=%d H=%d does not fit the persistent kernel", N, H);
