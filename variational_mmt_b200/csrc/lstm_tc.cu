@@ -5,25 +5,31 @@
 //
 // The batch rows of a recurrence are independent, so they are split into G groups of <= 16 rows.  One
 // thread-block CLUSTER of C = ceil(H/32) CTAs (<= 16, one per SM) serves one (direction, group) for the whole
-// sequence with no global-memory round trip per step:
+// sequence with no global-memory round trip and NO cluster-wide barrier per step:
 //   * CTA c owns 32 hidden units = 128 gate rows [i(32) f(32) g(32) o(32)] of W_hh.  Its 128 x Kp slice stays
-//     resident in shared memory as fp16 (K-major, 128B swizzle).  fp16 carries the same 11 significand bits as
-//     TF32, which is what a tensor-core "fp32" GEMM rounds its operands to; accumulation is fp32 in TMEM;
-//     c / h state stays fp32 in registers, h is rounded to fp16 only as next step's MMA operand.
-//   * forward step : D[128 gate rows, 16 batch cols] = W_slice[128,Kp] * h_{t-1}^T  (32 tcgen05.mma M128 N16 K16)
-//                    -> tcgen05.ld -> gates regrouped through shared memory -> sigmoid/tanh cell update fused in
-//                    the epilogue -> the CTA's new h slice is broadcast as 16-byte DSMEM stores straight into
-//                    the B-operand tile of all C CTAs (double buffered) -> one cluster barrier.
-//   * backward step: the SAME resident slice read MN-major gives A = W_slice^T: each CTA contracts its own 128
-//                    gate rows, partial dh[512 units, batch] = W_slice^T * dG_t^T (dG enters as fp16 hi + lo
-//                    columns of dG * 2^12: 22 significand bits, no gradient magnitude is lost), the partials are reduce-scattered through
-//                    DSMEM to the unit owners and summed in a fixed order (deterministic) after one cluster
-//                    barrier.
+//     resident in TENSOR MEMORY as fp16 for the whole sequence (A operand of tcgen05.mma from TMEM).  fp16 carries
+//     the same 11 significand bits as TF32, which is what a tensor-core "fp32" GEMM rounds its operands to;
+//     accumulation is fp32 in TMEM; c / h state stays fp32 in registers, h is rounded to fp16 only as the next
+//     step's MMA operand.
+//   * forward step : D[128 gate rows, 16 batch cols] = W_slice[128,Kp] * h_{t-1}^T  (Kp/16 tcgen05.mma M128 N16 K16,
+//                    four independent accumulator chains) -> tcgen05.ld -> gates regrouped through shared memory ->
+//                    sigmoid/tanh cell update fused in the epilogue -> the CTA's new fp16 h slice (1 KB, contiguous in
+//                    the un-swizzled K-major operand tile) goes to every CTA of the cluster as ONE bulk async copy
+//                    per destination (cp.async.bulk shared::cta -> shared::cluster) that completes on the
+//                    destination's mbarrier.  The MMA warp of each CTA waits on that mbarrier only: producer ->
+//                    consumer data flow replaces the barrier, and both ends of the hand-off are in the async proxy.
+//   * backward step: the SAME slice transposed (A = W_slice^T, resident in TMEM): each CTA contracts its own 128
+//                    gate rows, partial dh[512 units, batch] = W_slice^T * dG_t^T (dG enters as fp16 hi + lo columns
+//                    of dG * 2^12: 22 significand bits, no gradient magnitude is lost); the partials are
+//                    reduce-scattered to the unit owners with one 2 KB bulk copy per owner, again signalled through
+//                    mbarriers, and summed in a fixed order (deterministic).
+// Double buffering + the data dependence of the recurrence itself make every buffer reuse safe (see the comments
+// at the copies).
 #include <cuda.h>
 #include <cuda_fp16.h>
-#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <stdio.h>
+#include <mutex>
 #include "common.cuh"
 #include "vmmt_internal.h"
 #include "lstm_tc.h"
@@ -33,10 +39,9 @@ namespace {
 constexpr int UC = 32;                 // hidden units per CTA
 constexpr int NP = 16;                 // batch columns per cluster (MMA N)
 constexpr int THREADS = 160;           // warps 0-3: epilogue / cell owners, warp 4: MMA issuer
-constexpr int A_BLOCK = 128 * 128;     // one k-block of the resident slice: 128 rows x 64 fp16 = 16 KB
-constexpr int B_BLOCK = NP * 128;      // one k-block of the h tile: 16 rows x 64 fp16 = 2 KB
-constexpr int NCH = 4;                 // independent accumulator chains (a dependent tcgen05.mma chain is latency bound at N = 16)
 constexpr float DG_SCALE = 4096.0f;    // backward: dG enters the MMA as fp16 hi + lo of dG * 2^12
+constexpr uint32_t TMEM_COLS = 512;    // whole tensor memory: the allocation then starts at column 0
+constexpr uint32_t TMEM_D = 256;       // accumulators; columns [0,256) hold the weight slice
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -45,18 +50,25 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -69,13 +81,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+// shared::cta -> shared::cluster bulk copy, completion (bytes) signalled on an mbarrier of the destination CTA
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -85,22 +94,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(tmem_c), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-  const __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-// fast transcendental forms for the tensor-core path (their ~1e-6 error is far below the operand rounding)
-__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -123,20 +125,38 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bits
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// fast transcendental forms for the tensor-core path (their ~1e-6 error is far below the operand rounding)
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+// shared-memory matrix descriptors (sm_100 version bits).
+//   swizzled  : K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO); LBO unused
+//   unswizzled: K-major core matrices (8 rows x 16 B, 128 B contiguous); LBO = byte distance between core matrices
+//               adjacent in K, SBO = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t make_desc_none(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
   return d;
 }
 // byte offset of the 16-byte chunk holding elements [8*chunk, 8*chunk+8) of row `row` in a [rows][64 x 2B]
 // 128B-swizzled block
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
-
 struct TcFwdParams {
   VmmtLstmDir d[2];
   const int64_t* lengths;
@@ -147,30 +167,12 @@ struct TcBwdParams {
   VmmtLstmDirBwd d[2];
   const int64_t* lengths;
   int T, N, H, C, G, Ng, Kp;
+  long long* trace;
 };
 
-// resident slice: row r = gate*32 + unit  <-  W_hh[gate*H + u0 + unit, 0:H] as fp16, zero padded
-__device__ __forceinline__ void load_w_slice(uint8_t* A, const float* __restrict__ w_hh, int H, int Kp, int u0) {
-  const int chunks_per_row = Kp / 8;
-  for (int e = threadIdx.x; e < 128 * chunks_per_row; e += blockDim.x) {
-    const int r = e / chunks_per_row, ci = e % chunks_per_row;
-    const int gate = r >> 5, unit = u0 + (r & 31);
-    __align__(16) __half hv[8];
-    const int k0 = ci * 8;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = k0 + i;
-      const float w = (unit < H && k < H) ? __ldg(w_hh + ((size_t)gate * H + unit) * H + k) : 0.0f;
-      hv[i] = __float2half_rn(w);
-    }
-    *reinterpret_cast<uint4*>(A + (size_t)(ci >> 3) * A_BLOCK + sw_off(r, ci & 7)) = *reinterpret_cast<uint4*>(hv);
-  }
-}
-
-// TS mode: the slice lives in TMEM as the MMA's A operand (lane = row, one 32-bit column = two consecutive k).
+// The slice lives in TMEM as the MMA's A operand (lane = row, one 32-bit column = two consecutive k).
 // forward: row r = gate*32 + unit (warp = gate, lane = unit), columns k/2 for k in [0, Kp)
-__device__ __forceinline__ void load_w_tmem_fwd(uint32_t tmem_a, const float* __restrict__ w_hh, int H, int Kp, int u0,
-                                                int warp, int lane) {
+__device__ __forceinline__ void load_w_tmem_fwd(const float* __restrict__ w_hh, int H, int Kp, int u0, int warp, int lane) {
   const int unit = u0 + lane;
   const float* row = w_hh + ((size_t)warp * H + min(unit, H - 1)) * H;
   const bool vec = (H & 3) == 0;
@@ -194,13 +196,12 @@ __device__ __forceinline__ void load_w_tmem_fwd(uint32_t tmem_a, const float* __
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = pack_h2(f[2 * i], f[2 * i + 1]);
-    tmem_st_x16(tmem_a + ((uint32_t)(32 * warp) << 16) + (uint32_t)(c * 16), pk);
+    tmem_st_x16(((uint32_t)(32 * warp) << 16) + (uint32_t)(c * 16), pk);
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 // backward: A = W_slice^T: tile mt, row = unit 128 mt + 32 warp + lane, columns j/2 for this CTA's 128 gate rows j
-__device__ __forceinline__ void load_w_tmem_bwd(uint32_t tmem_a, const float* __restrict__ w_hh, int H, int u0, int n_mt,
-                                                int warp, int lane) {
+__device__ __forceinline__ void load_w_tmem_bwd(const float* __restrict__ w_hh, int H, int u0, int n_mt, int warp, int lane) {
   for (int mt = 0; mt < n_mt; ++mt) {
     const int u = 128 * mt + 32 * warp + lane;
     for (int gate = 0; gate < 4; ++gate) {
@@ -212,30 +213,41 @@ __device__ __forceinline__ void load_w_tmem_bwd(uint32_t tmem_a, const float* __
         const float b = (u < H && ul1 < H) ? __ldg(w_hh + ((size_t)gate * H + ul1) * H + u) : 0.f;
         pk[i] = pack_h2(a, b);
       }
-      tmem_st_x16(tmem_a + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 64 + gate * 16), pk);
+      tmem_st_x16(((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 64 + gate * 16), pk);
     }
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <bool TS>
+// NRG = 8-row groups of batch columns per cluster (MMA N = 8 NRG): 1 when the group has <= 8 rows, else 2.
+// The bytes a CTA sends per step (C copies of 512 NRG B) are what bounds the hand-off (DSMEM ~20 B/clk/SM).
+template <int NRG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdParams P) {
+  constexpr int NPc = 8 * NRG;                               // batch columns of the MMA
+  constexpr int RM = 2 * NRG;                                // cells per thread (rows warp + 4 r)
+  constexpr uint32_t CHUNK = NRG * 128;                      // one k-chunk (8 k) of the h tile: NRG core matrices
+  constexpr uint32_t SLICE = 4 * CHUNK;                      // one CTA's h slice: 32 units = 4 k-chunks, contiguous
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const int Kp = P.Kp, nkb = Kp / 64;
-  const uint32_t a_bytes = TS ? 0u : (uint32_t)nkb * A_BLOCK;   // SS mode: resident slice in shared memory
-  uint8_t* A = sm;                                          // [nkb][128][128 B]
-  uint8_t* Bt = A + a_bytes;                                // [2][nkb][NP][128 B]
-  float* gsm = reinterpret_cast<float*>(Bt + (size_t)2 * nkb * B_BLOCK);   // [4][NP][32]
-  __half* hstage = reinterpret_cast<__half*>(gsm + 4 * NP * 32);          // [NP][32]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(hstage + NP * 32);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const uint32_t tile_bytes = (uint32_t)(Kp / 8) * CHUNK;    // one h operand tile [Kp/8 chunks][NRG][8 rows][8 fp16]
+  uint8_t* Bt = sm;                                          // [2][tile]
+  float* gsm = reinterpret_cast<float*>(Bt + 2 * tile_bytes);                 // [4 gates][NPc][32]
+  uint8_t* hstage = reinterpret_cast<uint8_t*>(gsm + 4 * NPc * 32);           // [2][SLICE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hstage + 2 * SLICE);           // [0] mma_done, [1..2] h_full[buf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const uint32_t bt_addr = base;
+  const uint32_t hstage_addr = smem_u32(hstage);
+  const uint32_t bar_mma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
+  auto ht_off = [](int n, int k) -> uint32_t {               // byte offset of element (row n, k) in a tile / slice
+    return (uint32_t)(k >> 3) * CHUNK + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int C = P.C;
-  const int cl = blockIdx.x / C;                            // cluster index = (dir, group)
+  const int cl = blockIdx.x / C;                             // cluster index = (dir, group)
   const int crank = (int)cluster_rank();
   const int dir = cl / P.G, grp = cl % P.G;
   const VmmtLstmDir& D = P.d[dir];
@@ -245,50 +257,50 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   const int u0 = crank * UC;
 
   if (P.trace && blockIdx.x == 0 && tid == 0) { P.trace[8] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.trace[11] = (long long)g; }
-  if (!TS) load_w_slice(A, D.w_hh, H, Kp, u0);
-  // h_{-1}: every CTA fills its own operand tile (buffer 0) from h0; rows >= nn and k >= H are zero
-  for (int e = tid; e < 2 * nkb * NP * 8; e += blockDim.x) {
-    const int bufi = e / (nkb * NP * 8), rem = e % (nkb * NP * 8);
-    const int kb = rem / (NP * 8), row = (rem / 8) % NP, ch = rem % 8;
+  // h_{-1}: every CTA fills its own operand tile (buffer 0) from h0; rows >= nn and k >= H are zero in both buffers
+  for (int e = tid; e < 2 * (Kp / 8) * NPc; e += blockDim.x) {
+    const int bufi = e / ((Kp / 8) * NPc), rem = e % ((Kp / 8) * NPc);
+    const int chunk = rem / NPc, row = rem % NPc;
     __align__(16) __half hv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = kb * 64 + ch * 8 + i;
+      const int k = chunk * 8 + i;
       const float v = (bufi == 0 && D.h0 && row < nn && k < H) ? D.h0[(size_t)(n0 + row) * H + k] : 0.0f;
       hv[i] = __float2half_rn(v);
     }
-    *reinterpret_cast<uint4*>(Bt + (size_t)bufi * nkb * B_BLOCK + (size_t)kb * B_BLOCK + sw_off(row, ch)) =
-        *reinterpret_cast<uint4*>(hv);
+    *reinterpret_cast<uint4*>(Bt + (size_t)bufi * tile_bytes + ht_off(row, chunk * 8)) = *reinterpret_cast<uint4*>(hv);
   }
+  for (int e = tid; e < 2 * (int)SLICE / 16; e += blockDim.x) reinterpret_cast<uint4*>(hstage)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(smem_u32(bar), 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_full0, 1);
+    mbar_init(bar_full0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    if (TS) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
-    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(64));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy smem writes -> visible to the MMA
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + (TS ? 256u : 0u);     // TS: columns [0,256) hold the weight slice
-  if (TS && warp < 4) {
-    load_w_tmem_fwd(tmem_base, D.w_hh, H, Kp, u0, warp, lane);
+  if (*tmem_slot != 0u) __trap();                            // the whole TMEM was requested: the base must be column 0
+  if (warp < 4) {
+    load_w_tmem_fwd(D.w_hh, H, Kp, u0, warp, lane);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
 
-  // cell ownership: thread (warp q < 4, lane) owns cells (n = q + 4 r, unit = lane), r = 0..3
-  float c[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f}, bias[4][4];
-  int len[4];
+  // cell ownership: thread (warp q < 4, lane) owns cells (n = q + 4 r, unit = lane), r < nr <= RM (nr is warp-uniform)
+  float c[RM], h[RM], bias[RM][4];
+  int len[RM];
   const int unit = u0 + lane;
   const bool ulive = warp < 4 && unit < H;
+  const int nr = (warp < 4 && nn > warp) ? (nn - warp + 3) / 4 : 0;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < RM; ++r) {
     const int n = warp + 4 * r;
-    len[r] = T;
+    len[r] = T; c[r] = 0.f; h[r] = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[r][g] = 0.f;
     if (ulive && n < nn) {
@@ -304,9 +316,11 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
       if (P.lengths) len[r] = (int)P.lengths[gn];
     }
   }
-  // instruction descriptor: D f32, A/B fp16 K-major, N = 16, M = 128
-  const uint32_t idesc = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  cluster_sync_all();          // every CTA of the cluster is initialised before any remote store lands
+  const int ucl = min(unit, H - 1);                          // clamped: dead lanes read valid memory, results discarded
+  // instruction descriptor: D f32, A/B fp16 K-major, N = NPc, M = 128
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const bool leader = elect_one();
+  cluster_sync_all();          // every CTA of the cluster is initialised (tiles, mbarriers) before any remote copy lands
   if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[9] = clock64();
 
   for (int s = 0; s < T; ++s) {
@@ -315,113 +329,126 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
     const bool tr = P.trace != nullptr && blockIdx.x == 0 && s == 5;
     if (tr && tid == 0) P.trace[0] = clock64();
     if (warp == 4) {
-      if (lane == 0) {
-        if (tr) P.trace[13] = clock64();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tr) P.trace[14] = clock64();
-        const uint32_t a0 = base, b0 = base + a_bytes + buf * nkb * B_BLOCK;
-        for (int kb = 0; kb < nkb; ++kb) {
+      // arm next step's hand-off barrier: C slices will land in the other tile
+      if (leader && s + 1 < T) mbar_arrive_expect_tx(bar_full0 + 8u * (uint32_t)(buf ^ 1), (uint32_t)C * SLICE);
+      if (s > 0) mbar_wait(bar_full0 + 8u * (uint32_t)buf, (uint32_t)(((s - 1) >> 1) & 1));   // h_{s-1} of all CTAs landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tr && lane == 0) P.trace[14] = clock64();
+      const uint32_t b0 = bt_addr + (uint32_t)buf * tile_bytes;
+      for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                     // k-step j of block kb accumulates into chain j
-            const uint64_t bd = make_desc(b0 + kb * B_BLOCK + j * 32, 16, 1024);
-            if (TS) {
-              umma_f16_ts(tmem_d + j * NP, tmem_base + (uint32_t)(kb * 32 + j * 8), bd, idesc, kb > 0 ? 1u : 0u);
-            } else {
-              const uint64_t ad = make_desc(a0 + kb * A_BLOCK + j * 32, 16, 1024);
-              umma_f16(tmem_d + j * NP, ad, bd, idesc, kb > 0 ? 1u : 0u);
-            }
-          }
+        for (int j = 0; j < 4; ++j) {                       // k-step j of block kb accumulates into chain j
+          // un-swizzled K-major: core matrices adjacent in K are CHUNK apart (LBO), 8-row groups 128 B apart (SBO)
+          const uint64_t bd = make_desc_none(b0 + (uint32_t)(kb * 8 + j * 2) * CHUNK, CHUNK, 128u);
+          if (leader) umma_f16_ts(TMEM_D + j * NPc, (uint32_t)(kb * 32 + j * 8), bd, idesc, kb > 0 ? 1u : 0u);
         }
-        umma_commit(smem_u32(bar));
-        if (tr) P.trace[1] = clock64();
       }
+      if (leader) umma_commit(bar_mma);
+      if (tr && lane == 0) P.trace[1] = clock64();
       __syncwarp();
     } else {
       // input-projection terms of this step (independent of the recurrence: issued before the wait)
-      float gx[4][4];
+      float gx[RM][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int n = warp + 4 * r;
+      for (int r = 0; r < RM; ++r) {
+        const int n = min(warp + 4 * r, nn - 1);
+        const float* gp = D.gx + ((size_t)t * N + n0 + n) * 4 * H + ucl;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) gx[r][g] = 0.f;
-        if (ulive && n < nn) {
-          const float* gp = D.gx + ((size_t)t * N + n0 + n) * 4 * H + unit;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) gx[r][g] = __ldg(gp + (size_t)g * H);
-        }
+        for (int g = 0; g < 4; ++g) gx[r][g] = (r < nr) ? __ldg(gp + (size_t)g * H) + bias[r][g] : 0.f;
       }
       if (tr && tid == 0) P.trace[2] = clock64();
-      mbar_wait(smem_u32(bar), (uint32_t)(s & 1));
+      mbar_wait(bar_mma, (uint32_t)(s & 1));
       if (tr && tid == 0) P.trace[3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float acc[NP];
+      float acc[NPc];
       {
-        uint32_t v[32];                                     // chains 0,1 then 2,3: 4 x 16 columns
-        tmem_ld_x32(tmem_d + ((uint32_t)(32 * warp) << 16), v);
+        uint32_t v[32];                                     // 4 chains x NPc columns
+        tmem_ld_x32(TMEM_D + ((uint32_t)(32 * warp) << 16), v);
+        if (NRG == 2) {
 #pragma unroll
-        for (int n = 0; n < NP; ++n) acc[n] = __uint_as_float(v[n]) + __uint_as_float(v[NP + n]);
-        tmem_ld_x32(tmem_d + ((uint32_t)(32 * warp) << 16) + 2 * NP, v);
+          for (int n = 0; n < NPc; ++n) acc[n] = __uint_as_float(v[n]) + __uint_as_float(v[NPc + n]);
+          tmem_ld_x32(TMEM_D + ((uint32_t)(32 * warp) << 16) + 2 * NPc, v);
 #pragma unroll
-        for (int n = 0; n < NP; ++n) acc[n] += __uint_as_float(v[n]) + __uint_as_float(v[NP + n]);
+          for (int n = 0; n < NPc; ++n) acc[n] += __uint_as_float(v[n]) + __uint_as_float(v[NPc + n]);
+        } else {
+#pragma unroll
+          for (int n = 0; n < NPc; ++n)
+            acc[n] = (__uint_as_float(v[n]) + __uint_as_float(v[8 + n])) + (__uint_as_float(v[16 + n]) + __uint_as_float(v[24 + n]));
+        }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // accumulator reads precede the next step's MMAs
 #pragma unroll
-      for (int n = 0; n < NP; ++n) gsm[(warp * NP + n) * 32 + lane] = acc[n];   // gate `warp`, unit `lane`
+      for (int n = 0; n < NPc; ++n) gsm[(warp * NPc + n) * 32 + lane] = acc[n];   // gate `warp`, unit `lane`
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tr && tid == 0) P.trace[4] = clock64();
+      uint8_t* hs = hstage + (size_t)buf * SLICE;
+      float av[RM][4], hout[RM];                             // activated gates / masked output, stored after the hand-off
+      // straight-line (branch-free) cell updates so the RM independent dependency chains interleave
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int n = warp + 4 * r;
-        float hn16 = 0.f;
-        if (ulive && n < nn) {
-          const float Gi = gsm[(0 * NP + n) * 32 + lane] + gx[r][0] + bias[r][0];
-          const float Gf = gsm[(1 * NP + n) * 32 + lane] + gx[r][1] + bias[r][1];
-          const float Gg = gsm[(2 * NP + n) * 32 + lane] + gx[r][2] + bias[r][2];
-          const float Go = gsm[(3 * NP + n) * 32 + lane] + gx[r][3] + bias[r][3];
-          const float ig = fsigmoid(Gi), fg = fsigmoid(Gf), gg = ftanh(Gg), og = fsigmoid(Go);
-          const float cn = fg * c[r] + ig * gg;
-          const float hn = og * ftanh(cn);
+      for (int r = 0; r < RM; ++r) {
+        if (r < nr) {                                        // warp-uniform
+          const int n = warp + 4 * r;
+          const float Gi = gsm[(0 * NPc + n) * 32 + lane] + gx[r][0];
+          const float Gf = gsm[(1 * NPc + n) * 32 + lane] + gx[r][1];
+          const float Gg = gsm[(2 * NPc + n) * 32 + lane] + gx[r][2];
+          const float Go = gsm[(3 * NPc + n) * 32 + lane] + gx[r][3];
+          av[r][0] = fsigmoid(Gi); av[r][1] = fsigmoid(Gf); av[r][2] = ftanh(Gg); av[r][3] = fsigmoid(Go);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        if (r < nr) {
+          const int n = warp + 4 * r;
+          const float cn = av[r][1] * c[r] + av[r][0] * av[r][2];
+          const float hn = av[r][3] * ftanh(cn);
           const bool m = t < len[r];
-          if (m) { c[r] = cn; h[r] = hn; }
+          c[r] = m ? cn : c[r];
+          h[r] = m ? hn : h[r];
+          hout[r] = m ? hn : 0.f;
+          *reinterpret_cast<__half*>(hs + ht_off(n, lane)) = __float2half_rn(ulive ? h[r] : 0.f);
+        }
+      }
+      if (tr && tid == 0) P.trace[13] = clock64();
+      if (s + 1 < T) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // staged slice -> visible to the bulk-copy engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tr && tid == 0) P.trace[5] = clock64();
+        // One copy per destination CTA (own CTA included) into the OTHER operand tile, completing on the
+        // destination's h_full barrier.  Reuse is safe without further synchronisation: a destination's tile
+        // (buf^1) was last read by its MMAs of step s-1, which completed before that CTA produced the h_{s-1}
+        // slice this CTA had to receive before computing h_s; hstage[buf] is rewritten at step s+2, after this
+        // CTA received every h_{s+1} slice, each produced after the producer consumed this copy.
+        const int dstc = (lane < 4) ? warp * 4 + lane : 99;  // 4 copies per warp
+        if (dstc < C) {
+          const uint32_t dst = mapa(bt_addr + (uint32_t)(buf ^ 1) * tile_bytes + (uint32_t)crank * SLICE, (uint32_t)dstc);
+          const uint32_t bar = mapa(bar_full0 + 8u * (uint32_t)(buf ^ 1), (uint32_t)dstc);
+          bulk_copy_to_cluster(dst, hstage_addr + (uint32_t)buf * SLICE, SLICE, bar);
+        }
+      }
+      if (tr && tid == 0) P.trace[6] = clock64();
+      // outputs and the tensors saved for backward leave after the hand-off: off the recurrence's critical path
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        const int n = warp + 4 * r;
+        if (ulive && r < nr) {
           const size_t row = (size_t)t * N + n0 + n;
-          D.out[row * D.out_ld + unit] = m ? hn : 0.f;
+          D.out[row * D.out_ld + unit] = hout[r];
           if (D.gates) {
             float* gp = D.gates + row * 4 * H + unit;
-            gp[0] = ig; gp[(size_t)H] = fg; gp[(size_t)2 * H] = gg; gp[(size_t)3 * H] = og;
+            gp[0] = av[r][0]; gp[(size_t)H] = av[r][1]; gp[(size_t)2 * H] = av[r][2]; gp[(size_t)3 * H] = av[r][3];
           }
           if (D.cs) D.cs[row * H + unit] = c[r];
-          hn16 = h[r];
         }
-        hstage[n * 32 + lane] = __float2half_rn(hn16);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tr && tid == 0) P.trace[5] = clock64();
-      if (s + 1 < T) {
-        // broadcast this CTA's h slice (nn rows x 32 units = 4 chunks of 16 B per row) into the operand tile
-        // (other buffer) of every CTA of the cluster, own CTA included
-        const int kb = u0 >> 6, ch0 = (u0 & 63) >> 3;
-        const uint32_t dst_local = base + a_bytes + (buf ^ 1) * nkb * B_BLOCK + kb * B_BLOCK;
-        // thread -> (row n, chunk cj) = tid & 63, destinations (tid >> 6) + 2 i
-        const int n = (tid & 63) >> 2, cj = tid & 3;
-        if (n < nn) {
-          const uint4 val = *reinterpret_cast<const uint4*>(hstage + n * 32 + cj * 8);
-          const uint32_t off = dst_local + sw_off(n, ch0 + cj);
-          for (int dstc = tid >> 6; dstc < C; dstc += 2) st_cluster_v4(mapa(off, (uint32_t)dstc), val);
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      if (tr && tid == 0) P.trace[6] = clock64();
     }
-    if (s + 1 < T) cluster_sync_all();
     if (tr && tid == 0) P.trace[7] = clock64();
   }
   if (P.trace && blockIdx.x == 0 && tid == 0) { P.trace[10] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.trace[12] = (long long)g; }
   if (warp < 4) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < RM; ++r) {
       const int n = warp + 4 * r;
-      if (ulive && n < nn) {
+      if (ulive && r < nr) {
         if (D.hT) D.hT[(size_t)(n0 + n) * H + unit] = h[r];
         if (D.cT) D.cT[(size_t)(n0 + n) * H + unit] = c[r];
       }
@@ -429,26 +456,27 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
-    if (TS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(64));
-  }
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(TMEM_COLS));
   cluster_sync_all();          // no CTA exits while a peer could still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <bool TS>
+template <int NRG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdParams P) {
+  constexpr int NPc = 8 * NRG;
+  constexpr int RM = 2 * NRG;
+  constexpr int KB_BYTES = 2 * NPc * 128;                    // one k-block (64 gate rows) of the dG tile: hi rows | lo rows
+  constexpr int PART = NPc * 32 * 4;                         // one (source, owner) block of dh partials
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const int Kp = P.Kp, nkb = Kp / 64;
-  const uint32_t a_bytes = TS ? 0u : (uint32_t)nkb * A_BLOCK;
-  uint8_t* A = sm;                                          // [nkb][128][128 B]  (same resident slice as forward)
-  uint8_t* Bt = A + a_bytes;                                // [2 k-blocks][2*NP rows][128 B]: dG hi rows 0..15, lo rows 16..31
-  float* recv = reinterpret_cast<float*>(Bt + 2 * (2 * NP) * 128);       // [2][16 src][NP][32]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(recv + 2 * 16 * NP * 32);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* Bt = sm;                                          // [2 k-blocks][2 NPc rows][128 B] swizzled: dG hi rows 0..NPc-1, lo rows NPc..
+  float* recv = reinterpret_cast<float*>(Bt + 2 * KB_BYTES);              // [2][16 src][NPc][32]
+  float* stage = recv + 2 * 16 * NPc * 32;                                // [2][16 owners][NPc][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * 16 * NPc * 32);// [0] mma_done, [1..2] recv_full[buf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const uint32_t recv_addr = smem_u32(recv), stage_addr = smem_u32(stage);
+  const uint32_t bar_mma = smem_u32(bars), bar_recv0 = smem_u32(bars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int C = P.C;
@@ -460,39 +488,41 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   const int n0 = grp * P.Ng;
   const int nn = min(P.Ng, N - n0);
   const int u0 = crank * UC;
+  const uint32_t part_bytes = (uint32_t)nn * 128u;           // only the rows that exist travel
 
-  if (!TS) load_w_slice(A, D.w_hh, H, Kp, u0);
-  for (int e = tid; e < 2 * (2 * NP) * 128 / 16; e += blockDim.x) reinterpret_cast<uint4*>(Bt)[e] = make_uint4(0, 0, 0, 0);
-  for (int e = tid; e < 2 * 16 * NP * 32; e += blockDim.x) recv[e] = 0.f;
+  if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[8] = clock64();
+  for (int e = tid; e < 2 * KB_BYTES / 16; e += blockDim.x) reinterpret_cast<uint4*>(Bt)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(smem_u32(bar), 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_recv0, 1);
+    mbar_init(bar_recv0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    if (TS) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
-    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("fence.proxy.async;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + (TS ? 256u : 0u);
+  if (*tmem_slot != 0u) __trap();
   const int n_mt = (P.C * UC + 127) / 128;                  // 128-unit output tiles that hold real units
-  if (TS && warp < 4) {
-    load_w_tmem_bwd(tmem_base, D.w_hh, H, u0, n_mt, warp, lane);
+  if (warp < 4) {
+    load_w_tmem_bwd(D.w_hh, H, u0, n_mt, warp, lane);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
 
-  float dc[4] = {0.f, 0.f, 0.f, 0.f}, dhr[4] = {0.f, 0.f, 0.f, 0.f};
-  int len[4];
+  float dc[RM], dhr[RM];
+  int len[RM];
   const int unit = u0 + lane;
   const bool ulive = warp < 4 && unit < H;
+  const int ucl = min(unit, H - 1);
+  const int nr = (warp < 4 && nn > warp) ? (nn - warp + 3) / 4 : 0;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < RM; ++r) {
     const int n = warp + 4 * r;
-    len[r] = T;
+    len[r] = T; dc[r] = 0.f; dhr[r] = 0.f;
     if (ulive && n < nn) {
       const int gn = n0 + n;
       if (D.dcT) dc[r] = D.dcT[(size_t)gn * H + unit];
@@ -500,119 +530,183 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       if (P.lengths) len[r] = (int)P.lengths[gn];
     }
   }
-  // D f32, A fp16 MN-major (W_slice^T), B fp16 K-major, N = 32 (hi | lo), M = 128
-  const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | ((uint32_t)((2 * NP) >> 3) << 17) |
-                         ((uint32_t)(128 >> 4) << 24);
-  const uint32_t idesc_ts = idesc & ~(1u << 15);            // A from TMEM has no major bit
+  // D f32, A fp16 from TMEM (W_slice^T), B fp16 K-major, N = 2 NPc (hi | lo), M = 128
+  const uint32_t idesc = (1u << 4) | ((uint32_t)((2 * NPc) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const bool leader = elect_one();
   cluster_sync_all();
+  if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[9] = clock64();
+
+  // Everything of a step that does not depend on the incoming dh is loaded one step ahead (the loads are issued
+  // before the MMA wait, the arithmetic runs while the reduce-scatter is in flight):
+  //   pf[r] = {a1, b0, b1, b2, b3, fg, dout},  dh = dh_rec + dout,  dct = dc + dh a1,
+  //   dG = {dct b0, dct b1, dct b2, dh b3},  dc' = dct fg.
+  float pf[RM][7];
+  auto load_raw = [&](int sp) {                              // raw {ig, fg, gg, og, ct, cp, dout}: loads only (branch-free)
+    const int tq = D.reverse ? sp : T - 1 - sp;
+    const int tp = D.reverse ? tq + 1 : tq - 1;
+    const bool has_prev = tp >= 0 && tp < T;
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      if (r < nr) {
+        const int gn = n0 + warp + 4 * r;
+        const size_t row = (size_t)tq * N + gn;
+        const float* gp = D.gates + row * 4 * H + ucl;
+        pf[r][0] = __ldg(gp); pf[r][1] = __ldg(gp + (size_t)H); pf[r][2] = __ldg(gp + (size_t)2 * H); pf[r][3] = __ldg(gp + (size_t)3 * H);
+        pf[r][4] = __ldg(D.cs + row * H + ucl);
+        pf[r][5] = has_prev ? __ldg(D.cs + ((size_t)tp * N + gn) * H + ucl) : (D.c0 ? __ldg(D.c0 + (size_t)gn * H + ucl) : 0.f);
+        pf[r][6] = D.dout ? __ldg(D.dout + row * D.dout_ld + ucl) : 0.f;
+      }
+    }
+  };
+  auto derive = [&]() {                                      // raw -> {a1, b0, b1, b2, b3, fg, dout}
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      if (r < nr) {
+        const float ig = pf[r][0], fg = pf[r][1], gg = pf[r][2], og = pf[r][3], ct = pf[r][4], cp = pf[r][5];
+        const float tc = ftanh(ct);
+        pf[r][0] = og * (1.f - tc * tc);
+        pf[r][1] = gg * ig * (1.f - ig);
+        pf[r][2] = cp * fg * (1.f - fg);
+        pf[r][3] = ig * (1.f - gg * gg);
+        pf[r][4] = tc * og * (1.f - og);
+        pf[r][5] = fg;
+      }
+    }
+  };
+  if (warp < 4) { load_raw(0); derive(); }
 
   for (int s = 0; s < T; ++s) {
     const int t = D.reverse ? s : T - 1 - s;
     const int buf = s & 1;
     const bool last = (s + 1 == T);
+    const bool tr = P.trace != nullptr && blockIdx.x == 0 && s == 5;
+    if (tr && tid == 0) P.trace[0] = clock64();
+    float dGs[RM][4];
     if (warp < 4) {
-      // ---- elementwise BPTT of this CTA's cells -> dG_t (global, and bf16 hi/lo operand rows n / 16+n)
+      // ---- elementwise BPTT of this CTA's cells -> dG_t as fp16 hi/lo operand rows n / NPc+n
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int n = warp + 4 * r;
-        float dG[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ulive && n < nn) {
-          const int gn = n0 + n;
-          const size_t row = (size_t)t * N + gn;
-          if (t < len[r]) {
-            const float* gp = D.gates + row * 4 * H + unit;
-            const float ig = gp[0], fg = gp[(size_t)H], gg = gp[(size_t)2 * H], og = gp[(size_t)3 * H];
-            const float ct = D.cs[row * H + unit];
-            const int tp = D.reverse ? t + 1 : t - 1;
-            float cp;
-            if (tp >= 0 && tp < T) cp = D.cs[((size_t)tp * N + gn) * H + unit];
-            else cp = D.c0 ? D.c0[(size_t)gn * H + unit] : 0.f;
-            const float dh = dhr[r] + (D.dout ? D.dout[row * D.dout_ld + unit] : 0.f);
-            const float tc = ftanh(ct);
-            const float dct = dc[r] + dh * og * (1.f - tc * tc);
-            dG[0] = dct * gg * ig * (1.f - ig);
-            dG[1] = dct * cp * fg * (1.f - fg);
-            dG[2] = dct * ig * (1.f - gg * gg);
-            dG[3] = dh * tc * og * (1.f - og);
-            dc[r] = dct * fg;
-            dhr[r] = 0.f;                                   // consumed; the next value comes from the reduce below
-          }                                                 // else: frozen state, dhr passes through unchanged
-          float* dg = D.dgates + row * 4 * H + unit;
-          dg[0] = dG[0]; dg[(size_t)H] = dG[1]; dg[(size_t)2 * H] = dG[2]; dg[(size_t)3 * H] = dG[3];
-        }
-        // operand tile: k = gate*32 + lane (this CTA's 128 gate rows), row n (hi) and NP + n (lo)
+      for (int r = 0; r < RM; ++r) {
+        if (r < nr) {
+          const int n = warp + 4 * r;
+          const bool m = ulive && t < len[r];
+          const float dh = dhr[r] + pf[r][6];
+          const float dct = dc[r] + dh * pf[r][0];
+          dGs[r][0] = m ? dct * pf[r][1] : 0.f;
+          dGs[r][1] = m ? dct * pf[r][2] : 0.f;
+          dGs[r][2] = m ? dct * pf[r][3] : 0.f;
+          dGs[r][3] = m ? dh * pf[r][4] : 0.f;
+          dc[r] = m ? dct * pf[r][5] : dc[r];
+          dhr[r] = m ? 0.f : dhr[r];                        // consumed (the next value comes from the reduce below) / frozen: passes through
+          // operand tile: k = gate*32 + lane (this CTA's 128 gate rows), row n (hi) and NPc + n (lo)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          // fp16 hi + lo of dG * 2^12: 22 significand bits, magnitudes from 1.5e-11 to 16 (clamped beyond)
-          const float xs = fminf(fmaxf(dG[g] * DG_SCALE, -60000.f), 60000.f);
-          const __half hi = __float2half_rn(xs);
-          const __half lo = __float2half_rn(xs - __half2float(hi));
-          const int k = g * 32 + lane, kb = k >> 6, ch = (k & 63) >> 3, el = k & 7;
-          *reinterpret_cast<__half*>(Bt + kb * (2 * NP * 128) + sw_off(n, ch) + el * 2) = hi;
-          *reinterpret_cast<__half*>(Bt + kb * (2 * NP * 128) + sw_off(NP + n, ch) + el * 2) = lo;
-        }
-      }
-      asm volatile("fence.proxy.async;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    if (last && D.dh0 == nullptr) break;                    // the last dh_prev only feeds dh0
-    __syncthreads();
-    if (warp == 4) {
-      if (lane == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b0 = base + a_bytes;
-        for (int mt = 0; mt < n_mt; ++mt) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {                  // K = 128 gate rows = 8 steps of 16
-            const uint64_t bd = make_desc(b0 + (ks >> 2) * (2 * NP * 128) + (ks & 3) * 32, 16, 1024);
-            if (TS) {
-              umma_f16_ts(tmem_d + mt * 32, tmem_base + (uint32_t)(mt * 64 + ks * 8), bd, idesc_ts, ks > 0 ? 1u : 0u);
-            } else {
-              // A^T: M = units [128 mt, +128) = unit blocks 2 mt, 2 mt + 1 (LBO apart), K rows 16 ks.. (SBO = 8 rows)
-              const uint64_t ad = make_desc(base + (2 * mt) * A_BLOCK + ks * 2048, A_BLOCK, 1024);
-              umma_f16(tmem_d + mt * 32, ad, bd, idesc, ks > 0 ? 1u : 0u);
-            }
+          for (int g = 0; g < 4; ++g) {
+            // fp16 hi + lo of dG * 2^12: 22 significand bits, magnitudes from 1.5e-11 to 16 (clamped beyond)
+            const float xs = fminf(fmaxf(dGs[r][g] * DG_SCALE, -60000.f), 60000.f);
+            const __half hi = __float2half_rn(xs);
+            const __half lo = __float2half_rn(xs - __half2float(hi));
+            const int k = g * 32 + lane, kb = k >> 6, ch = (k & 63) >> 3, el = k & 7;
+            *reinterpret_cast<__half*>(Bt + kb * KB_BYTES + sw_off(n, ch) + el * 2) = hi;
+            *reinterpret_cast<__half*>(Bt + kb * KB_BYTES + sw_off(NPc + n, ch) + el * 2) = lo;
           }
         }
-        umma_commit(smem_u32(bar));
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    const bool stop = last && D.dh0 == nullptr;             // the last dh_prev only feeds dh0
+    if (!stop) __syncthreads();
+    if (tr && tid == 0) P.trace[1] = clock64();
+    if (warp == 4) {
+      if (stop) break;
+      if (leader) mbar_arrive_expect_tx(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)C * part_bytes);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int mt = 0; mt < n_mt; ++mt) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                    // K = 128 gate rows = 8 steps of 16
+          const uint64_t bd = make_desc_sw128(base + (uint32_t)(ks >> 2) * KB_BYTES + (uint32_t)(ks & 3) * 32u);
+          if (leader) umma_f16_ts(TMEM_D + mt * 32, (uint32_t)(mt * 64 + ks * 8), bd, idesc, ks > 0 ? 1u : 0u);
+        }
+      }
+      if (leader) umma_commit(bar_mma);
       __syncwarp();
     } else {
-      mbar_wait(smem_u32(bar), (uint32_t)(s & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // partial dh[unit = 128 mt + 32 warp + lane, n] -> owner CTA 4 mt + warp, slot recv[buf][src = crank][n][lane]
-      for (int mt = 0; mt < n_mt; ++mt) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_d + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 32), v);
-        const int owner = 4 * mt + warp;
-        if (owner < C) {
-          const uint32_t dst = mapa(smem_u32(recv) + (uint32_t)(((buf * 16 + crank) * NP) * 32 + lane) * 4u, (uint32_t)owner);
+      // dG_t leaves for global memory (it is d gx, consumed by the batched weight / input gradient GEMMs)
 #pragma unroll
-          for (int n = 0; n < NP; ++n)
-            if (n < nn) st_cluster_f32(dst + (uint32_t)n * 128u, (__uint_as_float(v[n]) + __uint_as_float(v[NP + n])) * (1.0f / DG_SCALE));
+      for (int r = 0; r < RM; ++r) {
+        if (ulive && r < nr) {
+          float* dg = D.dgates + ((size_t)t * N + n0 + warp + 4 * r) * 4 * H + unit;
+          dg[0] = dGs[r][0]; dg[(size_t)H] = dGs[r][1]; dg[(size_t)2 * H] = dGs[r][2]; dg[(size_t)3 * H] = dGs[r][3];
+        }
+      }
+      if (stop) break;
+      if (!last) load_raw(s + 1);                           // next step's saved activations: issued now, consumed after the hand-off
+      mbar_wait(bar_mma, (uint32_t)(s & 1));
+      if (tr && tid == 0) P.trace[2] = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // partial dh[unit = 128 mt + 32 warp + lane, n] -> staged per owner CTA 4 mt + warp as [n][lane]
+      float* st = stage + (size_t)buf * 16 * NPc * 32;
+      for (int mt = 0; mt < n_mt; ++mt) {
+        const int owner = 4 * mt + warp;
+        if (NRG == 2) {
+          uint32_t v[32];
+          tmem_ld_x32(TMEM_D + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 32), v);
+          if (owner < C) {
+#pragma unroll
+            for (int n = 0; n < NPc; ++n)
+              st[(owner * NPc + n) * 32 + lane] = (__uint_as_float(v[n]) + __uint_as_float(v[NPc + n])) * (1.0f / DG_SCALE);
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld_x16(TMEM_D + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 32), v);
+          if (owner < C) {
+#pragma unroll
+            for (int n = 0; n < NPc; ++n)
+              st[(owner * NPc + n) * 32 + lane] = (__uint_as_float(v[n]) + __uint_as_float(v[NPc + n])) * (1.0f / DG_SCALE);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    cluster_sync_all();
-    if (warp < 4) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tr && tid == 0) P.trace[3] = clock64();
+      // reduce-scatter: one block of nn rows per owner, into the owner's recv[buf][src = this CTA], completing on
+      // the owner's recv_full[buf].  stage[buf] / recv[buf] are reused at step s+2: by then this CTA has consumed
+      // every owner's step-(s+1) block, each sent after that owner consumed this step's copies.
+      const int dstc = (lane < 4) ? warp * 4 + lane : 99;
+      if (dstc < C) {
+        const uint32_t dst = mapa(recv_addr + (uint32_t)((buf * 16 + crank) * PART), (uint32_t)dstc);
+        const uint32_t bar = mapa(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)dstc);
+        bulk_copy_to_cluster(dst, stage_addr + (uint32_t)((buf * 16 + dstc) * PART), part_bytes, bar);
+      }
+      if (tr && tid == 0) P.trace[6] = clock64();
+      if (!last) derive();                                  // while the reduce-scatter is in flight
+      mbar_wait(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)((s >> 1) & 1));
+      if (tr && tid == 0) P.trace[4] = clock64();
+      const float* rb = recv + (size_t)buf * 16 * NPc * 32;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int n = warp + 4 * r;
-        if (ulive && n < nn) {
-          float sum = dhr[r];                               // non-zero only for frozen (masked) cells
-          for (int src = 0; src < C; ++src) sum += recv[((buf * 16 + src) * NP + n) * 32 + lane];
-          dhr[r] = sum;
+      for (int r = 0; r < RM; ++r) {
+        if (r < nr) {
+          const int n = warp + 4 * r;
+          float s0 = dhr[r], s1 = 0.f, s2 = 0.f, s3 = 0.f;  // dhr: non-zero only for frozen (masked) cells
+          for (int src = 0; src + 3 < C; src += 4) {
+            s0 += rb[((src + 0) * NPc + n) * 32 + lane];
+            s1 += rb[((src + 1) * NPc + n) * 32 + lane];
+            s2 += rb[((src + 2) * NPc + n) * 32 + lane];
+            s3 += rb[((src + 3) * NPc + n) * 32 + lane];
+          }
+          for (int src = C & ~3; src < C; ++src) s0 += rb[(src * NPc + n) * 32 + lane];
+          dhr[r] = (s0 + s1) + (s2 + s3);
         }
       }
     }
+    if (tr && tid == 0) P.trace[5] = clock64();
   }
+  if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[10] = clock64();
   if (warp < 4) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < RM; ++r) {
       const int n = warp + 4 * r;
-      if (ulive && n < nn) {
+      if (ulive && r < nr) {
         if (D.dh0) D.dh0[(size_t)(n0 + n) * H + unit] = dhr[r];
         if (D.dc0) D.dc0[(size_t)(n0 + n) * H + unit] = dc[r];
       }
@@ -620,53 +714,79 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
-    if (TS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
-  }
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(TMEM_COLS));
   cluster_sync_all();
 }
 
-struct TcPlan { int C, G, Ng, Kp; size_t smem_f, smem_b; };
+struct TcPlan { int C, G, Ng, Kp, nrg; };
 
-// weight slice in TMEM (default) or in shared memory (VMMT_LSTM_SS=1)
-bool tc_ts_mode() { static const bool ts = getenv("VMMT_LSTM_SS") == nullptr; return ts; }
+size_t fwd_smem(int Kp, int nrg) {
+  return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64;
+}
+size_t bwd_smem(int nrg) { return 1024 + (size_t)2 * 2 * 8 * nrg * 128 + (size_t)4 * 16 * 8 * nrg * 32 * 4 + 64; }
 
-bool tc_plan(int ndir, int N, int H, TcPlan* p) {
-  if (H < 32 || H > 512 || N < 1) return false;
+template <typename K>
+int prepare_kernel(K kernel, int C, size_t smem, int* max_clusters) {
+  // function attributes are sticky: set them once per (kernel, device); the co-resident cluster count is cached.
+  // Keyed by the kernel ADDRESS: the template instantiations share one function-pointer type.
+  struct Slot { const void* fn; int dev; size_t smem; int maxc[17]; };
+  static Slot slots[32];
+  static int nslots = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  Slot* sl = nullptr;
+  for (int i = 0; i < nslots; ++i)
+    if (slots[i].fn == (const void*)kernel && slots[i].dev == dev) sl = &slots[i];
+  if (!sl) {
+    if (nslots == 32) { vmmt_set_error("lstm_tc: kernel attribute cache full"); return VMMT_EINVAL; }
+    sl = &slots[nslots++];
+    sl->fn = (const void*)kernel; sl->dev = dev; sl->smem = 0;
+    for (int i = 0; i < 17; ++i) sl->maxc[i] = 0;
+    VMMT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
+  if (smem > sl->smem) {
+    VMMT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sl->smem = smem;
+    for (int i = 0; i < 17; ++i) sl->maxc[i] = 0;
+  }
+  if (sl->maxc[C] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+    sl->maxc[C] = n;
+  }
+  *max_clusters = sl->maxc[C];
+  return VMMT_OK;
+}
+
+bool tc_shape_ok(int ndir, int N, int H) {
+  return (ndir == 1 || ndir == 2) && H >= 32 && H <= 512 && N >= 1 && ceil_div(H, UC) <= 16;
+}
+
+// batch groups: as many clusters as can be co-resident (one wave; a cluster of 16 needs a whole GPC), at most 16
+// rows per group; groups of <= 8 rows run the N = 8 variant (half the hand-off bytes)
+void tc_plan(int ndir, int N, int H, int max_clusters, TcPlan* p) {
   p->C = ceil_div(H, UC);
-  if (p->C > 16) return false;
   p->Kp = ceil_div(H, 64) * 64;
-  // as many groups as there are cluster slots (one CTA per SM), at most 16 rows per group
-  const int slots = max(1, vmmt_num_sms() / (p->C * ndir));
-  int G = min(min(slots, 8), N);
+  const char* e = getenv("VMMT_LSTM_GROUPS");
+  int gmax = e ? atoi(e) : max(1, max_clusters / ndir);
+  int G = max(1, min(gmax, N));
   int Ng = ceil_div(N, G);
-  if (Ng > NP) { Ng = NP; }
-  G = ceil_div(N, Ng);
-  p->G = G; p->Ng = Ng;
-  const int nkb = p->Kp / 64;
-  const size_t a_bytes = tc_ts_mode() ? 0 : (size_t)nkb * A_BLOCK;
-  p->smem_f = 1024 + a_bytes + (size_t)2 * nkb * B_BLOCK + 4 * NP * 32 * 4 + NP * 32 * 2 + 64;
-  p->smem_b = 1024 + a_bytes + 2 * (2 * NP) * 128 + (size_t)2 * 16 * NP * 32 * 4 + 64;
-  return p->smem_f <= 227 * 1024 && p->smem_b <= 227 * 1024;
+  if (Ng > NP) Ng = NP;
+  p->Ng = Ng;
+  p->G = ceil_div(N, Ng);
+  p->nrg = Ng <= 8 ? 1 : 2;
 }
 
 template <typename K, typename PT>
 int cluster_launch(K kernel, const PT& params, int grid, int C, size_t smem, cudaStream_t s, const char* what) {
-  // function attributes are sticky: set them once per (kernel, device) and only raise the smem limit when needed
-  static size_t smem_set[64] = {0};
-  static bool np_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  if (smem > smem_set[dev]) {
-    VMMT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[dev] = smem;
-  }
-  if (C > 8 && !np_set[dev]) {
-    VMMT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    np_set[dev] = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -680,49 +800,85 @@ int cluster_launch(K kernel, const PT& params, int grid, int C, size_t smem, cud
   return vmmt_check_launch(what);
 }
 
-}  // namespace
-
-bool vmmt_lstm_tc_supported(int ndir, int N, int H) {
-  TcPlan p;
-  return (ndir == 1 || ndir == 2) && tc_plan(ndir, N, H, &p);
+long long* trace_buf() {
+  static long long* tbuf = nullptr;
+  if (!tbuf) { cudaMalloc(&tbuf, 256); cudaMemset(tbuf, 0, 256); }
+  return tbuf;
 }
 
+template <int NRG>
+int launch_fwd(TcFwdParams& P, const TcPlan& p, int ndir, int maxc, cudaStream_t s) {
+  const size_t smem = fwd_smem(p.Kp, NRG);
+  int dummy = 0;
+  int rc = prepare_kernel(lstm_tc_fwd_kernel<NRG>, p.C, smem, &dummy);
+  if (rc) return rc;
+  if (!getenv("VMMT_LSTM_TRACE"))
+    return cluster_launch(lstm_tc_fwd_kernel<NRG>, P, ndir * p.G * p.C, p.C, smem, s, "lstm_tc_fwd_kernel");
+  P.trace = trace_buf();
+  rc = cluster_launch(lstm_tc_fwd_kernel<NRG>, P, ndir * p.G * p.C, p.C, smem, s, "lstm_tc_fwd_kernel");
+  cudaStreamSynchronize(s);
+  long long h[16];
+  cudaMemcpy(h, P.trace, 128, cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[lstm fwd trace] T=%d C=%d G=%d Ng=%d nrg=%d max_clusters=%d setup %lld cyc, loop %lld cyc (%lld per step), block0 wall %lld ns\n",
+          P.T, p.C, p.G, p.Ng, NRG, maxc, h[9] - h[8], h[10] - h[9], (h[10] - h[9]) / P.T, h[12] - h[11]);
+  fprintf(stderr, "[lstm fwd trace] step5: mma warp h_full %lld issued %lld | epi: gx_loaded %lld mma_done %lld gates_xchg %lld cells %lld fence+bar %lld copies_issued %lld end %lld\n",
+          h[14] - h[0], h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[13] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0]);
+  return rc;
+}
+
+template <int NRG>
+int launch_bwd(TcBwdParams& P, const TcPlan& p, int ndir, int maxc, cudaStream_t s) {
+  const size_t smem = bwd_smem(NRG);
+  int dummy = 0;
+  int rc = prepare_kernel(lstm_tc_bwd_kernel<NRG>, p.C, smem, &dummy);
+  if (rc) return rc;
+  if (!getenv("VMMT_LSTM_TRACE"))
+    return cluster_launch(lstm_tc_bwd_kernel<NRG>, P, ndir * p.G * p.C, p.C, smem, s, "lstm_tc_bwd_kernel");
+  P.trace = trace_buf();
+  rc = cluster_launch(lstm_tc_bwd_kernel<NRG>, P, ndir * p.G * p.C, p.C, smem, s, "lstm_tc_bwd_kernel");
+  cudaStreamSynchronize(s);
+  long long h[16];
+  cudaMemcpy(h, P.trace, 128, cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[lstm bwd trace] T=%d C=%d G=%d Ng=%d nrg=%d max_clusters=%d setup %lld cyc, loop %lld cyc (%lld per step)\n",
+          P.T, p.C, p.G, p.Ng, NRG, maxc, h[9] - h[8], h[10] - h[9], (h[10] - h[9]) / P.T);
+  fprintf(stderr, "[lstm bwd trace] step5: dG_ready %lld mma_done %lld staged %lld copies_issued %lld recv_full %lld end %lld\n",
+          h[1] - h[0], h[2] - h[0], h[3] - h[0], h[6] - h[0], h[4] - h[0], h[5] - h[0]);
+  return rc;
+}
+
+}  // namespace
+
+bool vmmt_lstm_tc_supported(int ndir, int N, int H) { return tc_shape_ok(ndir, N, H); }
+
 int vmmt_lstm_tc_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, cudaStream_t s) {
+  if (!tc_shape_ok(ndir, N, H)) return VMMT_EINVAL;
   TcPlan p;
-  if (!tc_plan(ndir, N, H, &p)) return VMMT_EINVAL;
+  const int Kp = ceil_div(H, 64) * 64;
+  int maxc = 1;
+  int rc = prepare_kernel(lstm_tc_fwd_kernel<2>, ceil_div(H, UC), fwd_smem(Kp, 2), &maxc);
+  if (rc) return rc;
+  tc_plan(ndir, N, H, maxc, &p);
   TcFwdParams P;
   for (int d = 0; d < ndir; ++d) P.d[d] = dirs[d];
   if (ndir == 1) P.d[1] = dirs[0];
   P.lengths = lengths;
   P.T = T; P.N = N; P.H = H; P.C = p.C; P.G = p.G; P.Ng = p.Ng; P.Kp = p.Kp;
   P.trace = nullptr;
-  static long long* tbuf = nullptr;
-  if (getenv("VMMT_LSTM_TRACE")) {
-    if (!tbuf) cudaMalloc(&tbuf, 128);
-    P.trace = tbuf;
-    int rc = tc_ts_mode() ? cluster_launch(lstm_tc_fwd_kernel<true>, P, ndir * p.G * p.C, p.C, p.smem_f, s, "lstm_tc_fwd_kernel")
-                          : cluster_launch(lstm_tc_fwd_kernel<false>, P, ndir * p.G * p.C, p.C, p.smem_f, s, "lstm_tc_fwd_kernel");
-    cudaStreamSynchronize(s);
-    long long h[16];
-    cudaMemcpy(h, tbuf, 128, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[lstm trace] mma warp: start %lld after_fence %lld issued %lld\n", h[13] - h[0], h[14] - h[0], h[1] - h[0]);
-    fprintf(stderr, "[lstm trace] T=%d setup %lld cycles, loop %lld cycles (%lld per step), wall %lld ns\n", T, h[9] - h[8], h[10] - h[9], (h[10] - h[9]) / T, h[12] - h[11]);
-    fprintf(stderr, "[lstm trace] C=%d G=%d Ng=%d step5 cycles: mma_issued %lld | epi: wait_start %lld mma_done %lld gates_xchg %lld cells %lld dsmem %lld cluster_bar %lld\n",
-            p.C, p.G, p.Ng, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0]);
-    return rc;
-  }
-  return tc_ts_mode() ? cluster_launch(lstm_tc_fwd_kernel<true>, P, ndir * p.G * p.C, p.C, p.smem_f, s, "lstm_tc_fwd_kernel")
-                      : cluster_launch(lstm_tc_fwd_kernel<false>, P, ndir * p.G * p.C, p.C, p.smem_f, s, "lstm_tc_fwd_kernel");
+  return p.nrg == 1 ? launch_fwd<1>(P, p, ndir, maxc, s) : launch_fwd<2>(P, p, ndir, maxc, s);
 }
 
 int vmmt_lstm_tc_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, cudaStream_t s) {
+  if (!tc_shape_ok(ndir, N, H)) return VMMT_EINVAL;
   TcPlan p;
-  if (!tc_plan(ndir, N, H, &p)) return VMMT_EINVAL;
+  int maxc = 1;
+  int rc = prepare_kernel(lstm_tc_bwd_kernel<2>, ceil_div(H, UC), bwd_smem(2), &maxc);
+  if (rc) return rc;
+  tc_plan(ndir, N, H, maxc, &p);
   TcBwdParams P;
   for (int d = 0; d < ndir; ++d) P.d[d] = dirs[d];
   if (ndir == 1) P.d[1] = dirs[0];
   P.lengths = lengths;
   P.T = T; P.N = N; P.H = H; P.C = p.C; P.G = p.G; P.Ng = p.Ng; P.Kp = p.Kp;
-  return tc_ts_mode() ? cluster_launch(lstm_tc_bwd_kernel<true>, P, ndir * p.G * p.C, p.C, p.smem_b, s, "lstm_tc_bwd_kernel")
-                      : cluster_launch(lstm_tc_bwd_kernel<false>, P, ndir * p.G * p.C, p.C, p.smem_b, s, "lstm_tc_bwd_kernel");
+  P.trace = nullptr;
+  return p.nrg == 1 ? launch_bwd<1>(P, p, ndir, maxc, s) : launch_bwd<2>(P, p, ndir, maxc, s);
 }
