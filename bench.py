@@ -202,17 +202,28 @@ def run_ours(args):
     def to_dev(h):
         return [t.to(dev, non_blocking=True) for t in h]
 
-    def step(d, read_stats):
-        src, sl, tgt, tl, img = d
+    graphed = None if args.no_graph else vm.GraphedTrainStep(model, loss_fn, shard_size=shard)
+
+    def eager_fwd_bwd(d):
+        src, sl, tgt, tl, img = [t.to(dev, non_blocking=True) for t in d]
         model.zero_grad()
         out, attns, _ = model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
         b = Bt()
         b.tgt, b.batch_size = tgt, B
-        st = loss_fn.sharded_compute_loss(b, out, attns, 0, tgt.size(0), shard, norm)
+        return loss_fn.sharded_compute_loss(b, out, attns, 0, tgt.size(0), shard, norm)._vec
+
+    def step(d, read_stats, force_eager=False):
+        """d: the batch, resident on the device (value) or in pinned host memory (e2e)."""
+        if graphed is not None and not force_eager:
+            # forward + loss + backward replayed from a CUDA graph (inputs copied into its static buffers);
+            # gradient all-reduce + clip + Adam issued normally
+            vec = graphed(*d, norm)
+        else:
+            vec = eager_fwd_bwd(d)
         optim.step()
         if read_stats:
-            return st._vec.cpu()                           # device->host read of the step's statistics
-        return st._vec
+            return vec.cpu()                               # device->host read of the step's statistics
+        return vec
 
     resident = [to_dev(h) for h in host]
     torch.cuda.synchronize()
@@ -230,7 +241,7 @@ def run_ours(args):
         tok = 0
         for i in range(nsteps):
             if e2e:
-                step(to_dev(host[i % NB]), True)
+                step(host[i % NB], True)
             else:
                 step(resident[i % NB], False)
             tok += tokens[i % NB]
@@ -256,9 +267,11 @@ def run_ours(args):
     sampler.start()
     l0 = _lib.lib.vmmt_launch_count()
     dev_ms, wall_ms, tok = timed(args.steps, e2e=False)
-    launches = _lib.lib.vmmt_launch_count() - l0
+    launches = _lib.lib.vmmt_launch_count() - l0          # eager launches (host-side counter)
+    if graphed is not None:                               # + the kernels each graph replay launches
+        launches += args.steps * graphed.kernels_per_replay
     for i in range(2):
-        step(to_dev(host[i % NB]), True)
+        step(host[i % NB], True)
     e2e_ms, e2e_wall, e2e_tok = timed(args.steps, e2e=True)
     clocks = sampler.stop()
     # host-side wall clock bounds the device time from above when the host is the bottleneck
@@ -268,7 +281,7 @@ def run_ours(args):
     # ---- per-call device time of the C-ABI entry points (one extra, untimed step)
     prof = []
     _lib.set_profile(prof)
-    step(resident[0], False)
+    step(resident[0], False, force_eager=True)
     torch.cuda.synchronize()
     _lib.set_profile(None)
     per_call = {}
@@ -299,6 +312,7 @@ def run_ours(args):
                        "gemm": "tf32 tcgen05 (fp32 storage, fp32 accumulate)" if _lib.lib.vmmt_get_gemm_mode() == 0
                                else "fp32 simt",
                        "parallelism": "dp%d" % n_gpus,
+                       "launch": "eager" if graphed is None else "cuda graph (fwd+loss+bwd) + eager all-reduce/clip/Adam",
                        "l2": "no flush: each step streams params+grads+Adam moments (%.0f MB) > 126 MB L2 and "
                              "rotates over %d different batches" % (16.0 * n_params / 1e6, NB)},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
@@ -367,6 +381,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

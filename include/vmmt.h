@@ -109,9 +109,14 @@ int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* leng
 int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
 int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, void* stream);
 int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
-int vmmt_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* Philox streams: effective offset = offset + (base ? *base : 0); `base` is a device-resident counter so that a
+ * captured CUDA graph draws fresh masks / noise on every replay (advance it with vmmt_counter_add). */
+int vmmt_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
+int vmmt_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                 const uint64_t* base /*device or NULL*/, void* stream);
 int vmmt_normal_sample(const float* mu, const float* sd, const float* eps /*or NULL: Philox*/, float* z,
-                       int64_t n, uint64_t seed, uint64_t offset, void* stream);
+                       int64_t n, uint64_t seed, uint64_t offset, const uint64_t* base /*device or NULL*/,
+                       void* stream);
 int vmmt_kl_fwd(const float* mu_q, const float* sd_q, const float* mu_p /*NULL: 0*/,
                 const float* sd_p /*NULL: 1*/, float* out1, int B, int Z, void* stream);
 int vmmt_kl_bwd(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, float* dmu_q,

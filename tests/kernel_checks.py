@@ -101,7 +101,7 @@ def check_lstm(tol=2e-5):
             lengths = torch.randint(1, T + 1, (N,), generator=torch.Generator().manual_seed(3)).sort(descending=True)[0]
             lengths[0] = T
             lengths = lengths.to(DEV)
-        o, hT, cT = ops.LSTMLayerFn.apply(x, h0, c0, rb, lengths, {"save": True}, *ws)
+        o, hT, cT = ops.lstm_layer(x, h0, c0, rb, lengths, {"save": True}, ws)
         wo, wh, wc = _r(T, N, ndir * H, seed=30), _r(ndir, N, H, seed=31), _r(ndir, N, H, seed=32)
         for w in ws:
             w.grad = None
@@ -170,7 +170,7 @@ def check_small_ops(tol=2e-5):
     w = torch.nn.Parameter(_r(V, E, seed=50))
     idx = torch.randint(0, V, (9, 7), generator=torch.Generator().manual_seed(1)).to(DEV)
     idx[0, 0] = 1
-    e = ops.EmbeddingFn.apply(idx, w, 1)
+    e = ops.embedding(idx, w, 1)
     g = _r(9, 7, E, seed=51)
     w.grad = None
     (e * g).sum().backward()
@@ -204,7 +204,7 @@ def check_small_ops(tol=2e-5):
             ("linear dadd", _rel(add.grad, ar.grad), tol)]
     # gate
     z = _r(8, 30, seed=59); gw = torch.nn.Parameter(_r(1, 30, scale=0.3, seed=60)); gb = torch.nn.Parameter(_r(1, seed=61))
-    gated = ops.GateFn.apply(z, gw, gb)
+    gated = ops.gate(z, gw, gb)
     gg = _r(8, 30, seed=62)
     gw.grad = None; gb.grad = None
     (gated * gg).sum().backward()
@@ -246,7 +246,7 @@ def check_loss(tol=2e-5):
                 t.grad = None
             W.grad = None; b.grad = None
             cfg = {"pad_idx": 1, "kl_weight": 0.7, "legacy_image_grad": legacy}
-            loss, stats = ops.VILossFn.apply(x, tg, W, b, mq, sq, mp, sp, loc, v, cfg)
+            loss, stats = ops.vi_loss(x, tg, W, b, mq, sq, mp, sp, loc, v, cfg)
             (loss / 40.0).backward()
             xr, Wr, br, mqr, sqr, locr = (t.detach().double().requires_grad_(True) for t in (x, W, b, mq, sq, loc))
             mpr = mp.detach().double().requires_grad_(True) if prior else torch.zeros(B, Z, device=DEV, dtype=torch.float64)

@@ -128,3 +128,51 @@ def test_h4_only_first_shard_is_scored(cuda_device):
     assert batch.tgt.shape[0] - 1 > 32
     n_all = int((batch.tgt[1:] != 1).sum())
     assert meta["stats"]["n_words"] == int((batch.tgt[1:33] != 1).sum()) < n_all
+
+
+def test_graphed_train_step_matches_eager_and_reference(cuda_device):
+    """GraphedTrainStep (forward + loss + backward replayed from a CUDA graph) gives the eager path's
+    gradients and the executed reference's statistics; a second replay on other inputs is not stale."""
+    meta, arr, cfg, params, batch = _setup("tiny_cond_train")
+    import variational_mmt_b200 as vm
+    model, fields = build_cuda_model(cfg, params)
+    model.train()
+    b = to_device(batch)
+    loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+    with vm.Normal.inject_noise(b.eps):
+        model.zero_grad()
+        out, attns, _ = model(b.src, b.tgt_in, b.src_lengths, b.tgt_lengths, b.img_feats)
+        st = loss.sharded_compute_loss(b, out, attns, 0, b.tgt.size(0), 32, b.batch_size)
+        eager = {k: v.copy() for k, v in named_grads(model).items() if v is not None}
+        step = vm.GraphedTrainStep(model, loss, shard_size=32)
+        vec = step(b.src, b.src_lengths, b.tgt_ids, b.tgt_lengths, b.img_feats, b.batch_size).cpu().numpy().copy()
+    ref = meta["stats"]
+    assert vec[0] == pytest.approx(ref["nmt"], rel=1e-3)
+    assert vec[3] == pytest.approx(ref["td_kl_before"], rel=1e-3)
+    assert int(round(vec[1])) == ref["n_words"]
+    assert vec[0] == pytest.approx(st.nmt_loss, rel=1e-6)
+    graphed = named_grads(model)
+    for k, g in eager.items():
+        assert relerr(graphed[k], g) <= 1e-6, k
+    # replay with a perturbed image feature: the image statistics must move, the NLL must not
+    with vm.Normal.inject_noise(b.eps):
+        vec2 = step(b.src, b.src_lengths, b.tgt_ids, b.tgt_lengths, b.img_feats.flip(0).contiguous(),
+                    b.batch_size).cpu().numpy().copy()
+    assert vec2[5] != vec[5] and step.kernels_per_replay > 50
+
+
+def test_graphed_step_draws_fresh_noise_each_replay(cuda_device):
+    """Dropout masks / latent noise come from Philox offsets relative to a device-resident counter: two
+    replays of the same captured graph on the same batch must not repeat the same masks."""
+    meta, arr, cfg, params, batch = _setup("tiny_cond_train")
+    import variational_mmt_b200 as vm
+    model, fields = build_cuda_model(cfg, params, dropout=0.5)
+    model.train()
+    b = to_device(batch)
+    loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+    step = vm.GraphedTrainStep(model, loss, shard_size=32)
+    args = (b.src, b.src_lengths, b.tgt_ids, b.tgt_lengths, b.img_feats, b.batch_size)
+    v1 = step(*args).cpu().numpy().copy()
+    v2 = step(*args).cpu().numpy().copy()
+    assert v1[0] != v2[0] and v1[3] != v2[3]
+    assert abs(v1[0] - v2[0]) < 0.2 * abs(v1[0])

@@ -153,7 +153,7 @@ class NMTVIModel1LossCompute(nn.Module):
         kw = self.kl_annealing_current if self.use_kl_annealing else 1.0
         cfg = {"pad_idx": self.padding_idx, "kl_weight": kw,
                "legacy_image_grad": self.image_grad == "legacy_passthrough"}
-        loss, stats = ops.VILossFn.apply(
+        loss, stats = ops.vi_loss(
             output.reshape(-1, output.size(2)), target.reshape(-1), lin.weight, lin.bias,
             qz_location.squeeze(0), qz_scale.squeeze(0),
             None if pz_location is None else pz_location.squeeze(0),

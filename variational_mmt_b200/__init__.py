@@ -15,5 +15,6 @@ from .ModelConstructor import make_vi_model_mmt, Generator
 from .modules import (Embeddings, LSTM, GlobalAttention, Normal, LocationLayer, ScaleLayer,
                       GlobalInferenceNetwork, GlobalFullInferenceNetwork, ImageGlobalInferenceNetwork)
 from .ops import manual_seed
+from .graph import GraphedTrainStep
 
 __version__ = "0.1.0"

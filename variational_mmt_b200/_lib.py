@@ -57,8 +57,9 @@ SIGNATURES = {
     "vmmt_act_bwd": (I, [P, P, P, L, I, P]),
     "vmmt_colsum_acc": (I, [P, L, I, I, P, P]),
     "vmmt_axpy": (I, [P, P, F, L, P]),
-    "vmmt_dropout": (I, [P, P, L, F, U64, U64, P]),
-    "vmmt_normal_sample": (I, [P, P, P, P, L, U64, U64, P]),
+    "vmmt_counter_add": (I, [P, U64, P]),
+    "vmmt_dropout": (I, [P, P, L, F, U64, U64, P, P]),
+    "vmmt_normal_sample": (I, [P, P, P, P, L, U64, U64, P, P]),
     "vmmt_kl_fwd": (I, [P, P, P, P, P, I, I, P]),
     "vmmt_kl_bwd": (I, [P, P, P, P, P, P, P, P, P, F, I, I, P]),
     "vmmt_gate_fwd": (I, [P, P, P, P, P, I, I, P]),

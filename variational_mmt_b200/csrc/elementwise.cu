@@ -84,7 +84,8 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 
 // ---------------------------------------------------------------- dropout (Philox, mask regenerated in bwd)
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
-                               uint64_t seed, uint64_t offset) {
+                               uint64_t seed, uint64_t offset, const uint64_t* __restrict__ base) {
+  if (base) offset += *base;                                  // device-resident step counter (CUDA-graph replays)
   const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
   const uint4 r = Philox(seed)((uint64_t)i4, offset);
@@ -101,7 +102,8 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
 // z = mu + sd * eps (Dists.py:21-26; eps injected or drawn from Philox via Box-Muller)
 __global__ void sample_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
                               const float* __restrict__ eps, float* __restrict__ z, int64_t n,
-                              uint64_t seed, uint64_t offset) {
+                              uint64_t seed, uint64_t offset, const uint64_t* __restrict__ base) {
+  if (base) offset += *base;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float e;
@@ -289,16 +291,23 @@ extern "C" int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void*
   axpy_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(y, x, alpha, n);
   return vmmt_check_launch("axpy");
 }
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { *ctr += inc; }
+
+extern "C" int vmmt_counter_add(uint64_t* ctr, uint64_t inc, void* stream) {
+  counter_add_kernel<<<1, 1, 0, ST(stream)>>>(ctr, inc);
+  return vmmt_check_launch("counter_add");
+}
+
 extern "C" int vmmt_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed,
-                            uint64_t offset, void* stream) {
+                            uint64_t offset, const uint64_t* base, void* stream) {
   if (n <= 0) return VMMT_OK;
   VMMT_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f outside [0,1)", (double)p);
-  dropout_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, ST(stream)>>>(x, y, n, p, seed, offset);
+  dropout_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, ST(stream)>>>(x, y, n, p, seed, offset, base);
   return vmmt_check_launch("dropout");
 }
 extern "C" int vmmt_normal_sample(const float* mu, const float* sd, const float* eps, float* z,
-                                  int64_t n, uint64_t seed, uint64_t offset, void* stream) {
-  sample_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(mu, sd, eps, z, n, seed, offset);
+                                  int64_t n, uint64_t seed, uint64_t offset, const uint64_t* base, void* stream) {
+  sample_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(mu, sd, eps, z, n, seed, offset, base);
   return vmmt_check_launch("normal_sample");
 }
 extern "C" int vmmt_kl_fwd(const float* mu_q, const float* sd_q, const float* mu_p,

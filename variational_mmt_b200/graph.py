@@ -1,0 +1,102 @@
+"""CUDA-graph capture of the forward + loss + backward of one training batch.
+
+The reference's trainer (onmt/TrainerMultimodal.py:625-718, ``_gradient_accumulation``) issues, per
+batch, ``model.zero_grad()`` -> ``model(src, tgt, lengths, tgt_lengths, img_feats)`` ->
+``train_loss.sharded_compute_loss(...)`` (which back-propagates) -> ``optim.step()``.  At batch 40 the
+~180 kernels of that sequence take less device time than Python needs to launch them, so the same
+sequence is captured ONCE per input-shape bucket (src_len, tgt_len, batch, normalization) into a CUDA
+graph and replayed: inputs are copied into static device buffers, the statistics come back in a static
+device vector.  The optimiser step (gradient all-reduce + clip + Adam: three launches) stays outside
+the graph so that the NCCL collective is issued normally.
+
+What makes replays differ from each other although every kernel argument is baked into the graph:
+the Philox offsets of dropout / latent noise are taken relative to a device-resident counter
+(``ops.rng_base``) that a one-thread kernel at the end of the graph advances.
+"""
+import torch
+
+from . import ops
+from . import _lib
+
+
+class _Batch(object):
+    """The two attributes NMTVIModel1LossCompute reads (TrainerMultimodal.py:668-677)."""
+
+    def __init__(self, tgt, batch_size):
+        self.tgt, self.batch_size = tgt, batch_size
+
+
+class GraphedTrainStep(object):
+    """forward + sharded loss + backward as a replayed CUDA graph.
+
+    step = GraphedTrainStep(model, loss_compute, shard_size=32)
+    stats_vec = step(src [S,B], src_lengths [B], tgt [Tf,B], tgt_lengths [B], img_feats [B,D], normalization)
+    optim.step()
+
+    ``stats_vec`` is a device tensor of 8 floats {nmt_loss, n_words, n_correct, kl, img_logprob, img_cos,
+    kl_after, elbo} (VIStatistics order) that is overwritten by the next call with the same shapes.
+    Inputs may live on the host (pinned) or on the device; they are copied into the graph's static buffers.
+    """
+
+    def __init__(self, model, loss_compute, shard_size=32, max_graphs=128):
+        assert not loss_compute.use_kl_annealing, \
+            "KL annealing changes a host-side weight every update: use the eager path"
+        self.model, self.loss = model, loss_compute
+        self.shard_size, self.max_graphs = shard_size, max_graphs
+        self._graphs = {}
+        self._pool = None
+        self.kernels_per_replay = 0          # libvmmt kernels inside the most recently captured graph
+        self.device = next(model.parameters()).device
+        ops.rng_base(self.device)
+
+    def _run(self, src, sl, tgt, tl, img, normalization):
+        self.model.zero_grad()
+        out, attns, _ = self.model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
+        st = self.loss.sharded_compute_loss(_Batch(tgt, tgt.size(1)), out, attns, 0, tgt.size(0),
+                                            self.shard_size, normalization)
+        return st._vec
+
+    def _capture(self, key, inputs, normalization):
+        if len(self._graphs) >= self.max_graphs:
+            raise RuntimeError("GraphedTrainStep: too many shape buckets; bucket the batches by length")
+        static = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in inputs]
+        for s, t in zip(static, inputs):
+            s.copy_(t, non_blocking=True)
+        n_updates = self.loss.n_model_updates
+        # warm-up on a side stream: lazy one-time work (function attributes, occupancy queries, allocator growth)
+        # must not happen inside the capture
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run(*static, normalization)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.lib.vmmt_launch_count()
+        with torch.cuda.graph(g, pool=self._pool):
+            ops.begin_step()
+            vec = self._run(*static, normalization)
+            ops.advance_rng()
+        self.kernels_per_replay = int(_lib.lib.vmmt_launch_count() - l0)
+        if self._pool is None:
+            self._pool = g.pool()
+        self.loss.n_model_updates = n_updates           # the warm-up / capture passes are not model updates
+        self._graphs[key] = (g, static, vec)
+        return self._graphs[key]
+
+    def __call__(self, src, src_lengths, tgt, tgt_lengths, img_feats, normalization):
+        if src.dim() == 3:
+            src = src[:, :, 0]
+        if tgt.dim() == 3:
+            tgt = tgt[:, :, 0]
+        inputs = (src, src_lengths, tgt, tgt_lengths, img_feats)
+        key = (tuple(src.shape), tuple(tgt.shape), tuple(img_feats.shape), float(normalization), self.model.training)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, inputs, normalization)
+        g, static, vec = entry
+        for s, t in zip(static, inputs):
+            s.copy_(t, non_blocking=True)
+        g.replay()
+        self.loss.n_model_updates += 1
+        return vec

@@ -21,7 +21,7 @@ class _Lut(nn.Module):
             self.weight[padding_idx].fill_(0)
 
     def forward(self, idx):
-        return ops.EmbeddingFn.apply(idx, self.weight, self.padding_idx)
+        return ops.embedding(idx, self.weight, self.padding_idx)
 
 
 class Embeddings(nn.Module):

@@ -51,8 +51,7 @@ class LSTM(nn.Module):
             h0 = hx[0][l * ndir:(l + 1) * ndir] if hx is not None else None
             c0 = hx[1][l * ndir:(l + 1) * ndir] if hx is not None else None
             cfg = {"save": save, "in_cols": in_cols if l == 0 else None}
-            x, hT, cT = ops.LSTMLayerFn.apply(x, h0, c0, in_bias if l == 0 else None, lengths, cfg,
-                                              *self._weights(l))
+            x, hT, cT = ops.lstm_layer(x, h0, c0, in_bias if l == 0 else None, lengths, cfg, self._weights(l))
             hs.append(hT)
             cs.append(cT)
         return x, (torch.cat(hs, 0), torch.cat(cs, 0))

@@ -89,7 +89,7 @@ class ImageGlobalInferenceNetwork(GlobalInferenceNetwork):
         self.gate_affine_transform = _Linear(latent_dim, 1)
 
     def forward(self, z, x=None, x_lengths=None):
-        gated = ops.GateFn.apply(z, self.gate_affine_transform.weight, self.gate_affine_transform.bias)
+        gated = ops.gate(z, self.gate_affine_transform.weight, self.gate_affine_transform.bias)
         loc = self.location(gated)
         # the scale branch never reaches the loss (VILoss.py:321): evaluate it only on demand
         return Normal(loc, lambda: self.scale(gated.detach()).detach()), None

@@ -14,18 +14,64 @@ from torch.autograd import Function
 from . import _lib as L
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, ACT_SOFTPLUS, ACT_SIGMOID, fptr, ptr, stream
 
-_seed_state = {"seed": 0x5EED, "offset": 0}
+_seed_state = {"seed": 0x5EED, "offset": 0, "base": None}
+RNG_STEP_STRIDE = 1 << 16          # Philox offsets reserved per step (>> dropout / sample calls in one step)
 
 
 def manual_seed(seed):
     """Seed of the in-kernel Philox streams (dropout masks, latent noise)."""
     _seed_state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
     _seed_state["offset"] = 0
+    if _seed_state["base"] is not None:
+        _seed_state["base"].zero_()
 
 
 def _next_offset():
     _seed_state["offset"] += 1
     return _seed_state["offset"]
+
+
+def rng_base(device=None):
+    """Device-resident step counter added to every Philox offset.  It exists so that a captured CUDA graph
+    (graph.py) draws fresh dropout masks / latent noise on each replay: the per-call offsets are baked into the
+    graph, the counter is advanced by a kernel at the end of it."""
+    if _seed_state["base"] is None:
+        _seed_state["base"] = torch.zeros(1, dtype=torch.int64, device=device or torch.device("cuda", torch.cuda.current_device()))
+    return _seed_state["base"]
+
+
+def _base_ptr():
+    b = _seed_state["base"]
+    return None if b is None else b.data_ptr()
+
+
+def begin_step():
+    """Restart the per-step call index (call at the top of a step that ends with advance_rng())."""
+    _seed_state["offset"] = 0
+
+
+def advance_rng():
+    L.call("vmmt_counter_add", rng_base().data_ptr(), RNG_STEP_STRIDE, stream())
+
+
+class _P(object):
+    """Hides a parameter from autograd's scan of Function inputs.
+
+    Parameter gradients are written by the backward kernels straight into ``param.grad``; autograd never
+    sees a gradient for them.  If the parameters were passed as tensor inputs, every Function node would
+    hold an edge to the parameter's AccumulateGrad node, and that node remembers the stream it was created
+    on: one created by an earlier eager forward (legacy default stream), kept alive by any live autograd
+    graph, makes the engine record an event on that stream at the end of a backward that runs inside a
+    CUDA-graph capture, which invalidates the capture.  Instead each Function takes a fresh zero-size
+    ``anchor`` leaf (so that its output requires grad even when only parameters do)."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
+def _anchor(device):
+    return torch.empty(0, device=device, requires_grad=True) if torch.is_grad_enabled() else None
 
 
 def grad_buf(p):
@@ -52,7 +98,8 @@ class EmbeddingFn(Function):
     """nn.Embedding lookup (onmt/modules/Embeddings.py:169-188)."""
 
     @staticmethod
-    def forward(ctx, idx, weight, pad_idx):
+    def forward(ctx, anchor, idx, weight, pad_idx):
+        weight = weight.t
         idx = idx.contiguous()
         n, E = idx.numel(), weight.shape[1]
         out = torch.empty(*idx.shape, E, device=weight.device, dtype=torch.float32)
@@ -68,14 +115,19 @@ class EmbeddingFn(Function):
         dout = dout.contiguous()
         L.call("vmmt_embedding_bwd", ptr(idx), idx.numel(), fptr(dout), w.shape[1], ctx.pad_idx,
                fptr(grad_buf(w)), stream())
-        return None, None, None
+        return None, None, None, None
+
+
+def embedding(idx, weight, pad_idx):
+    return EmbeddingFn.apply(_anchor(weight.device), idx, _P(weight), pad_idx)
 
 
 class LinearFn(Function):
     """y = act(x W[:, c0:c1]^T + b), optionally y = act(x W^T + b + addend) (nn.Linear + activation)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, cols, addend):
+    def forward(ctx, anchor, x, weight, bias, act, cols, addend):
+        weight, bias = weight.t, bias.t
         x2 = x.reshape(-1, x.shape[-1])
         if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < x2.shape[1]):
             x2 = x2.contiguous()
@@ -111,16 +163,16 @@ class LinearFn(Function):
         if bias is not None and bias.requires_grad:
             colsum_acc(dpre, M, N, grad_buf(bias))
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[1]:
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
             gemm(dpre, weight[:, c0:c1], dx, M, K, N, b_kmajor=False)                    # dx = dpre W
             dx = dx.view(ctx.xshape)
-        dadd = dpre.view(*ctx.xshape[:-1], N) if ctx.has_addend and ctx.needs_input_grad[5] else None
-        return dx, None, None, None, None, dadd
+        dadd = dpre.view(*ctx.xshape[:-1], N) if ctx.has_addend and ctx.needs_input_grad[6] else None
+        return None, dx, None, None, None, None, dadd
 
 
 def linear(x, weight, bias=None, act=ACT_NONE, cols=None, addend=None):
-    return LinearFn.apply(x, weight, bias, act, cols, addend)
+    return LinearFn.apply(_anchor(x.device), x, _P(weight), _P(bias), act, cols, addend)
 
 
 # --------------------------------------------------------------------------------------------
@@ -133,7 +185,8 @@ class LSTMLayerFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, h0, c0, rowbias, lengths, cfg, *weights):
+    def forward(ctx, anchor, x, h0, c0, rowbias, lengths, cfg, weights):
+        weights = weights.t
         ndir = len(weights) // 4
         T, N, In = x.shape
         Hd = weights[1].shape[1]
@@ -187,7 +240,7 @@ class LSTMLayerFn(Function):
         dhT = dhT.contiguous() if dhT is not None else None
         dcT = dcT.contiguous() if dcT is not None else None
         dg = torch.empty(ndir, T, N, 4 * Hd, device=dev, dtype=torch.float32)
-        need_h0 = h0 is not None and ctx.needs_input_grad[1]
+        need_h0 = h0 is not None and ctx.needs_input_grad[2]
         dh0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
         dc0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
         dirs = (L.LstmDirBwd * ndir)()
@@ -207,7 +260,7 @@ class LSTMLayerFn(Function):
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
         L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
         x2 = x.view(T * N, In)
-        dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         drow = None
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
@@ -234,13 +287,18 @@ class LSTMLayerFn(Function):
                 colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih))
             if b_hh.requires_grad:
                 colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_hh))
-        if rowbias is not None and ctx.needs_input_grad[3]:
+        if rowbias is not None and ctx.needs_input_grad[4]:
             drow = torch.zeros(N, 4 * Hd, device=dev, dtype=torch.float32)
             for d in range(ndir):                                      # the term enters every direction
                 colsum_acc(dg[d].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
         if dx is not None:
             dx = dx.view(T, N, In)
-        return (dx, dh0, dc0, drow, None, None) + (None,) * len(weights)
+        return None, dx, dh0, dc0, drow, None, None, None
+
+
+def lstm_layer(x, h0, c0, rowbias, lengths, cfg, weights):
+    """weights: (w_ih, w_hh, b_ih, b_hh) per direction."""
+    return LSTMLayerFn.apply(_anchor(x.device), x, h0, c0, rowbias, lengths, cfg, _P(tuple(weights)))
 
 
 def _rows(v):
@@ -310,14 +368,14 @@ class DropoutFn(Function):
         x = x.contiguous()
         y = torch.empty_like(x)
         ctx.p, ctx.seed, ctx.offset = p, _seed_state["seed"], _next_offset()
-        L.call("vmmt_dropout", fptr(x), fptr(y), x.numel(), p, ctx.seed, ctx.offset, stream())
+        L.call("vmmt_dropout", fptr(x), fptr(y), x.numel(), p, ctx.seed, ctx.offset, _base_ptr(), stream())
         return y
 
     @staticmethod
     def backward(ctx, dy):
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        L.call("vmmt_dropout", fptr(dy), fptr(dx), dy.numel(), ctx.p, ctx.seed, ctx.offset, stream())
+        L.call("vmmt_dropout", fptr(dy), fptr(dx), dy.numel(), ctx.p, ctx.seed, ctx.offset, _base_ptr(), stream())
         return dx, None
 
 
@@ -333,7 +391,7 @@ def normal_sample(mu, sd, eps=None):
         mu_c, sd_c = mu.detach().contiguous(), sd.detach().contiguous()
         z = torch.empty_like(mu_c)
         L.call("vmmt_normal_sample", fptr(mu_c), fptr(sd_c), fptr(eps.contiguous()) if eps is not None else None,
-               fptr(z), z.numel(), _seed_state["seed"], _next_offset(), stream())
+               fptr(z), z.numel(), _seed_state["seed"], _next_offset(), _base_ptr(), stream())
     return z
 
 
@@ -342,7 +400,8 @@ class GateFn(Function):
     (onmt/modules/NormalVariationalEncoder.py:286-299)."""
 
     @staticmethod
-    def forward(ctx, z, weight, bias):
+    def forward(ctx, anchor, z, weight, bias):
+        weight, bias = weight.t, bias.t
         z = z.contiguous()
         B, Z = z.shape
         gate = torch.empty(B, device=z.device, dtype=torch.float32)
@@ -360,7 +419,11 @@ class GateFn(Function):
         dpre = torch.empty(B, device=z.device, dtype=torch.float32)
         L.call("vmmt_gate_bwd", fptr(dgated), fptr(z), fptr(gate), fptr(dpre), fptr(grad_buf(ctx.weight)),
                fptr(grad_buf(ctx.bias)), B, Z, stream())
-        return None, None, None
+        return None, None, None, None
+
+
+def gate(z, weight, bias):
+    return GateFn.apply(_anchor(z.device), z, _P(weight), _P(bias))
 
 
 class VILossFn(Function):
@@ -373,6 +436,7 @@ class VILossFn(Function):
 
     @staticmethod
     def forward(ctx, out2d, target, gen_w, gen_b, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, cfg):
+        gen_w, gen_b = gen_w.t, gen_b.t
         dev = out2d.device
         out2d = out2d.contiguous()
         target = target.contiguous()
@@ -425,6 +489,10 @@ class VILossFn(Function):
         L.call("vmmt_image_loss_bwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(dloc), fptr(gs), 1.0,
                int(cfg.get("legacy_image_grad", True)), B, D, stream())
         return dx, None, None, None, dmq, dsq, dmp, dsp, dloc, None, None
+
+
+def vi_loss(out2d, target, gen_w, gen_b, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, cfg):
+    return VILossFn.apply(out2d, target, _P(gen_w), _P(gen_b), mu_q, sd_q, mu_p, sd_p, img_loc, img_v, cfg)
 
 
 def generator_logprobs(x2d, weight, bias):
