@@ -1,0 +1,6 @@
+"""Prior-only beam search for VI model 1 (reference: onmt/translate/TranslatorMultimodalVI.py,
+onmt/translate/Beam.py) with the beam bookkeeping on the device."""
+from .Beam import GNMTGlobalScorer
+from .TranslatorMultimodalVI import TranslatorMultimodalVI
+
+__all__ = ["TranslatorMultimodalVI", "GNMTGlobalScorer"]
