@@ -48,6 +48,11 @@ WORKLOADS = {
 }
 
 
+DECODE_DESC = ("translate_mm_vi.py prior-only beam search: conditional VI-model-1 (E=H=Z=500, V=10000), beam 5, "
+               "max_length 100, test-2016-sized set of 1000 synthetic sentences (lengths ~ clip(round(N(14,5)),3,50)), "
+               "random-init weights (no hypothesis ends early: every batch runs all 100 steps)")
+
+
 # ------------------------------------------------------------------------------------------------
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -331,6 +336,160 @@ def run_ours(args):
     return 0
 
 
+def cpu_decode_baseline(mk, n_sent, budget_s, beam=5, max_length=100):
+    """Oracle port of the reference's one-sentence-at-a-time beam search on the host cores."""
+    import torch
+    from oracle import synth, beam_ref
+    from oracle import vi_model1_ref as R
+    cfg = synth.ModelConfig(v_src=mk["v"], v_tgt=mk["v"], emb=mk["emb"], hidden=mk["hidden"], z_dim=mk["z"],
+                            conditional=mk["conditional"])
+    p = R._t(synth.make_params(cfg, 3435, 0.1))
+    b = synth.make_batch(cfg, batch_size=max(n_sent, 2), seed=11)
+    done, t0 = 0, time.perf_counter()
+    for i in range(n_sent):
+        n = int(b.src_lengths[i])
+        beam_ref.beam_search_one(p, cfg, torch.as_tensor(b.src[:n, i]), beam_size=beam, max_length=max_length)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "sentences/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d sentences, batch 1, beam %d, max_length %d, oracle port (torch %s CPU), %d threads"
+                      % (done, beam, max_length, torch.__version__, torch.get_num_threads())}
+
+
+def run_decode(args):
+    """--workload decode: beam-decode sentences/s (single GPU; replicas only -- sentences are independent)."""
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    mk = WORKLOADS["cfg1"][0]
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        torch.set_num_threads(os.cpu_count() or 1)
+        r = cpu_decode_baseline(mk, max(args.steps, 1), args.cpu_budget)
+        print(json.dumps({"impl": "reference", "metric": "beam_decode_sentences_per_sec", "value": r["value"],
+                          "unit": "sentences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": "decode", "desc": DECODE_DESC},
+                          "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "sentences/s",
+                                                     "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return 0
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import synthetic, _lib
+    opt = synthetic.make_opt(emb=mk["emb"], hidden=mk["hidden"], z_dim=mk["z"], conditional=True, dropout=0.5)
+    fields = synthetic.make_fields(mk["v"], mk["v"])
+    torch.manual_seed(3435)
+    model = vm.make_vi_model_mmt(opt, fields, gpu=True)
+    model.eval()
+    Bd = args.decode_batch
+    tr = vm.TranslatorMultimodalVI(model, fields, beam_size=5, n_best=1, max_length=100,
+                                   global_scorer=vm.GNMTGlobalScorer(0., -0.), cuda=True,
+                                   test_img_feats=np.zeros((1, 2048), np.float32), multimodal_model_type="vi-model1")
+    NB = 4
+
+    class Bt:
+        pass
+    host, resident = [], []
+    for i in range(NB):
+        src, sl, _t, _tl, _img = synthetic.random_batch(mk["v"], mk["v"], Bd, 8, seed=5000 + 97 * rank + i, pinned=True)
+        b = Bt(); b.batch_size = Bd; b.src = (src, sl)
+        host.append(b)
+        r = Bt(); r.batch_size = Bd; r.src = (src.to(dev), sl.to(dev))
+        resident.append(r)
+    h2d = host[0].src[0].numel() * 8 + host[0].src[1].numel() * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        d2h = 0
+        for i in range(n):
+            ret = tr.translate_batch((host if e2e else resident)[i % NB], None, None)
+            d2h = ret["steps"] * 5 * Bd * (8 + 4) + ret["steps"] * 5 * Bd * host[i % NB].src[0].size(0) * 4
+        ev1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([max(ev0.elapsed_time(ev1), wall)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), d2h
+    for i in range(max(args.warmup, 3)):
+        tr.translate_batch(resident[i % NB], None, None)
+    sampler = ClockSampler(_gpu_index_for_nvml(local_rank))
+    sampler.start()
+    l0 = _lib.lib.vmmt_launch_count()
+    ms, _ = timed(args.steps, False)
+    launches = _lib.lib.vmmt_launch_count() - l0
+    e2e_ms, d2h = timed(args.steps, True)
+    clocks = sampler.stop()
+    if rank == 0:
+        peaks, how = _peaks()
+        # dominant kernel: the generator with materialised log-probs (HBM bound: writes [K*B, V] fp32)
+        from variational_mmt_b200.ops import fptr, stream
+        R_, H, V = 5 * Bd, mk["hidden"], mk["v"]
+        x = torch.randn(R_, H, device=dev)
+        out = torch.empty(R_, V, device=dev)
+        lse = torch.empty(R_, device=dev)
+        gen = model.generator[0]
+        flush = torch.empty(64 * 1024 * 1024, device=dev)
+        ts = []
+        for it in range(13):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("vmmt_generator_logprobs", fptr(x), fptr(gen.weight), fptr(gen.bias), R_, H, V, fptr(out),
+                      fptr(lse), stream())
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(e0.elapsed_time(e1))
+        kms = sorted(ts)[len(ts) // 2]
+        alg = (R_ * V + V * H + R_ * H) * 4.0
+        ach = alg / (kms * 1e-3) / 1e9
+        roof = {"kernel": "vmmt_generator_logprobs (M=%d,H=%d,V=%d): GEMM + row log-sum-exp + normalise" % (R_, H, V),
+                "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": None, "ms": kms, "peak_source": how,
+                "algorithmic_bytes": "(M*V + V*H + M*H)*4: log-probs written once, weights and activations read once"}
+        cpu_b = None if args.no_cpu_baseline or world > 1 else cpu_decode_baseline(mk, 4, args.cpu_budget)
+        nsent = args.steps * Bd * world
+        print(json.dumps({
+            "metric": "beam_decode_sentences_per_sec", "value": nsent / (ms / 1e3), "unit": "sentences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "decode", "desc": DECODE_DESC, "sentences_per_step": Bd, "beam": 5,
+                       "parallelism": "replicas x%d (no collective)" % world,
+                       "l2": "log-probs [%d x %d] fp32 = %.0f MB per decode step are written and re-read each step; 4 "
+                             "different batches rotate" % (5 * Bd, mk["v"], 5 * Bd * mk["v"] * 4 / 1e6)},
+            "e2e": {"value": nsent / (e2e_ms / 1e3), "unit": "sentences/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_b}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
     """Times the dominant kernel of the step (the fused generator+NLL forward GEMM) in isolation with
     CUDA events on the launching stream and reports it against the measured tensor peak.  DESIGN.md
@@ -379,11 +538,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS) + ["decode"])
+    ap.add_argument("--decode-batch", type=int, default=250, help="sentences decoded together (workload decode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the baseline sample")
     args = ap.parse_args()
+    if args.workload == "decode":
+        return run_decode(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

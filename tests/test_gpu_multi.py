@@ -1,0 +1,69 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): the 2-rank NCCL step of the CUDA path equals gradient
+accumulation over the same two batches on one GPU (the reference's -accum_count 2 semantics)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import distributed as D
+    from gpu_helpers import build_cuda_model, to_device
+    from oracle import synth
+    D.init_from_env(backend="nccl", device=torch.device("cuda", rank))
+    cfg = synth.TINY
+    params = synth.make_params(cfg, 3435, 0.1)
+    model, fields = build_cuda_model(cfg, params)
+    model.train()
+    loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+    optim = vm.Optim("adam", 0.002, 5)
+    optim.set_parameters(model.parameters())
+    sizes = [5, 3]
+    batches = [synth.make_batch(cfg, batch_size=sizes[i], seed=100 + i, t_force=20) for i in range(2)]
+
+    def fwd_bwd(b, norm):
+        d = to_device(b, "cuda:%d" % rank)
+        with vm.Normal.inject_noise(d.eps):
+            out, attns, _ = model(d.src, d.tgt_in, d.src_lengths, d.tgt_lengths, d.img_feats)
+        return loss.sharded_compute_loss(d, out, attns, 0, d.tgt.size(0), 32, norm)
+
+    norm = D.global_normalization(batches[rank].batch_size, device="cuda:%d" % rank)
+    assert norm == sum(sizes)
+    accum = None
+    if rank == 0:                                    # the single-GPU accumulation this must equal
+        model.zero_grad()
+        for b in batches:
+            fwd_bwd(b, norm)
+        accum = optim.gflat.clone()
+    model.zero_grad()
+    st = fwd_bwd(batches[rank], norm)
+    optim.step()                                     # all-reduce (SUM) + clip + Adam
+    vec = D.reduce_statistics(st._vec)
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), g=optim.gflat.cpu().numpy(), p=optim.flat.cpu().numpy(),
+             vec=vec.cpu().numpy(), accum=(accum.cpu().numpy() if accum is not None else np.zeros(1)))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_two_gpu_step_equals_accumulation(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29850 + (os.getpid() % 100)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(2)]
+    assert np.array_equal(r0["g"], r1["g"]) and np.array_equal(r0["p"], r1["p"])      # replicas identical
+    rel = np.linalg.norm(r0["g"] - r0["accum"]) / np.linalg.norm(r0["accum"])
+    assert rel < 1e-5, rel
+    assert np.array_equal(r0["vec"], r1["vec"])

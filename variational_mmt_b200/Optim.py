@@ -4,11 +4,11 @@ Adam(eps=1e-9) over the flat buffers in two launches, with the data-parallel gra
 (NCCL, SUM -- SURVEY.md section 8e) issued on the same flat buffer right before it.
 """
 import torch
-import torch.distributed as dist
 
 from . import _lib as L
 from ._lib import fptr, stream
 from .flat import flatten_parameters
+from . import distributed
 
 
 class _ParamList(torch.nn.Module):
@@ -61,8 +61,8 @@ class Optim(object):
         if self.decay_method == "noam":
             self._set_rate(self.original_lr * (self.model_size ** (-0.5) *
                            min(self._step ** (-0.5), self._step * self.warmup_steps ** (-1.5))))
-        if self.sync_gradients and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM)
+        if self.sync_gradients:
+            distributed.all_reduce_gradients(self.gflat)
         n = self.flat.numel()
         max_norm = float(self.max_grad_norm) if self.max_grad_norm else 0.0
         if max_norm > 0:
