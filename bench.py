@@ -307,6 +307,33 @@ def run_ours(args):
             r = cpu_baseline.time_train_steps(mk, bk, steps=2, warmup=1, threads=cores, budget_s=args.cpu_budget)
             cpu_b = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "port",
                      "sample": r["sample"]}
+        # other entry points against their rooflines, from the per-call device times of the profiled eager step
+        others = {}
+        pc = dict(per_call)
+        H_, S_ = mk["hidden"], int(resident[0][0].size(0))
+        if "vmmt_adam_clip_step" in pc and "vmmt_sqnorm" in pc:
+            t = (pc["vmmt_adam_clip_step"][1] + pc["vmmt_sqnorm"][1]) * 1e-3
+            gbs = 32.0 * n_params / t / 1e9      # sqnorm reads g (4 B), Adam reads p,g,m,v and writes p,m,v (28 B)
+            others["clip+adam (vmmt_sqnorm + vmmt_adam_clip_step)"] = {
+                "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                "bytes": "32 B/param"}
+        if "vmmt_lstm_seq_fwd" in pc:
+            cnt, tot = pc["vmmt_lstm_seq_fwd"]
+            others["lstm recurrence fwd (vmmt_lstm_seq_fwd, %d launches)" % cnt] = {
+                "bound": "latency", "us_per_launch": 1e3 * tot / cnt,
+                "note": "sequential dependence: ~30 steps x (32 tcgen05.mma + cell update + DSMEM hand-off) per launch; "
+                        "neither the HBM nor the tensor roofline applies (8*N*H^2 = %.2f GFLOP per step)" % (8.0 * B * H_ * H_ / 1e9)}
+        if "vmmt_lstm_seq_bwd" in pc:
+            cnt, tot = pc["vmmt_lstm_seq_bwd"]
+            others["lstm recurrence bwd (vmmt_lstm_seq_bwd, %d launches)" % cnt] = {"bound": "latency", "us_per_launch": 1e3 * tot / cnt}
+        if "vmmt_attention_fwd" in pc:
+            cnt, tot = pc["vmmt_attention_fwd"]
+            Td = int(resident[0][2].size(0)) - 1
+            byts = 4.0 * (2 * B * Td * H_ + B * S_ * H_ + B * Td * S_)
+            gbs = byts * cnt / (tot * 1e-3) / 1e9
+            others["attention core fwd (vmmt_attention_fwd)"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                                                                 "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                                                 "bytes": "4*(2*B*T*H + B*S*H + B*T*S)"}
         line = {
             "metric": "train_target_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -328,6 +355,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu_b,
             "top_calls_ms": {k: round(v[1], 3) for k, v in top[:8]},
+            "roofline_others": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -107,7 +107,8 @@ int vmmt_masked_mean_fwd(const float* x, const int64_t* lengths, float* out, int
 int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* lengths, float* dx,
                          int accumulate, int T, int B, int H, void* stream);
 int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
-int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, void* stream);
+/* out[N] (+= column sums of a[M,N]); out2 (optional) receives the same sums (nn.LSTM's b_ih / b_hh pair). */
+int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, float* out2, void* stream);
 int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
 /* Philox streams: effective offset = offset + (base ? *base : 0); `base` is a device-resident counter so that a
  * captured CUDA graph draws fresh masks / noise on every replay (advance it with vmmt_counter_add). */
@@ -156,9 +157,14 @@ int vmmt_adam_clip_step(float* param, const float* grad, float* exp_avg, float* 
                         float beta1, float beta2, float eps, int64_t step, void* stream);
 
 /* ---- beam search bookkeeping (Beam.py:64-123; Models.py:589-594) */
-int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, int64_t eos, float* scores,
+/* step index = *step_dev when step_dev != NULL (device-resident: the decode step is replayed from a CUDA graph), else
+ * `step`; tok_cur / prev_cur ([K,B], optional) receive the newest tokens / back pointers at fixed addresses. */
+int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, const int64_t* step_dev, int64_t* tok_cur,
+                      int32_t* prev_cur, int64_t eos, float* scores,
                       int64_t* next_ys, int32_t* prev_ks, float* fin_score, int32_t* fin_t, int32_t* fin_k,
                       int32_t* n_fin, int32_t* done, int32_t* n_active, void* stream);
+/* hist[*step_dev][0:n] = cur[0:n]: the step's attention rows into the history the hypotheses are read from. */
+int vmmt_beam_record(const float* cur, float* hist, const int64_t* step_dev, int64_t n, void* stream);
 int vmmt_beam_reorder(const float* src, float* dst, const int32_t* prev_k_step, const int32_t* done, int L,
                       int K, int B, int H, void* stream);
 

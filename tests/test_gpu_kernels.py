@@ -19,3 +19,10 @@ def test_kernel_group(group, gemm_mode):
     fn = dict(kc.ALL)[group]
     bad = [(l, e, t) for l, e, t in fn() if not (e <= t * gemm_mode or (t == 0.0 and e == 0.0))]
     assert not bad, "\n".join(f"{l}: err {e:.3e} > tol {t * gemm_mode:.1e}" for l, e, t in bad)
+
+
+def test_lstm_stepwise_path(gemm_mode, monkeypatch):
+    """The large-batch path (one GEMM + one cell kernel per step, csrc/lstm_step.cu) on the same cases."""
+    monkeypatch.setenv("VMMT_LSTM_STEPWISE", "1")
+    bad = [(l, e, t) for l, e, t in kc.check_lstm() if not (e <= t * gemm_mode)]
+    assert not bad, "\n".join(f"{l}: err {e:.3e} > tol {t * gemm_mode:.1e}" for l, e, t in bad)

@@ -55,7 +55,7 @@ SIGNATURES = {
     "vmmt_masked_mean_fwd": (I, [P, P, P, L, I, I, I, P]),
     "vmmt_masked_mean_bwd": (I, [P, L, P, P, I, I, I, I, P]),
     "vmmt_act_bwd": (I, [P, P, P, L, I, P]),
-    "vmmt_colsum_acc": (I, [P, L, I, I, P, P]),
+    "vmmt_colsum_acc": (I, [P, L, I, I, P, P, P]),
     "vmmt_axpy": (I, [P, P, F, L, P]),
     "vmmt_counter_add": (I, [P, U64, P]),
     "vmmt_dropout": (I, [P, P, L, F, U64, U64, P, P]),
@@ -73,7 +73,8 @@ SIGNATURES = {
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),
     "vmmt_adam_clip_step": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),
-    "vmmt_beam_advance": (I, [P, I, I, I, I, L, P, P, P, P, P, P, P, P, P, P]),
+    "vmmt_beam_advance": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
+    "vmmt_beam_record": (I, [P, P, P, L, P]),
     "vmmt_beam_reorder": (I, [P, P, P, P, I, I, I, I, P]),
 }
 

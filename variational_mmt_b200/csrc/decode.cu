@@ -20,7 +20,11 @@ __device__ __forceinline__ bool better(float v, int i, float w, int j) {
 
 // One CTA per sentence.  logp [K*B, V] -> top-K of the flattened [K*V] candidate scores.
 __global__ void __launch_bounds__(256)
-beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int step, int64_t eos,
+beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int step_host,
+                    const int64_t* __restrict__ step_dev,   // device-resident step index (CUDA-graph replays) or null
+                    int64_t* __restrict__ tok_cur,          // [K,B] newest tokens (fixed address) or null
+                    int32_t* __restrict__ prev_cur,         // [K,B] newest back pointers (fixed address) or null
+                    int64_t eos,
                     float* __restrict__ scores,        // [B,K] running hypothesis scores (in/out)
                     int64_t* __restrict__ next_ys,     // [Lmax+1, K, B] tokens; slice `step` is the input
                     int32_t* __restrict__ prev_ks,     // [Lmax, K, B] back pointers
@@ -29,7 +33,11 @@ beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int ste
                     int32_t* __restrict__ n_fin, int32_t* __restrict__ done,    // [B]
                     int32_t* __restrict__ n_active) {
   const int b = blockIdx.x;
-  if (done[b]) return;
+  const int step = step_dev ? (int)*step_dev : step_host;
+  if (done[b]) {
+    if (threadIdx.x < K && prev_cur) prev_cur[threadIdx.x * B + b] = threadIdx.x;   // frozen sentence: identity reorder
+    return;
+  }
   __shared__ Cand cand[256 * KMAX];
   __shared__ Cand best[KMAX];
   __shared__ float rv[8];
@@ -89,6 +97,8 @@ beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int ste
       scores[b * K + k] = best[k].v;
       prev_ks[((size_t)step * K + k) * B + b] = pk;
       next_ys[((size_t)(step + 1) * K + k) * B + b] = tok;
+      if (tok_cur) tok_cur[(size_t)k * B + b] = tok;
+      if (prev_cur) prev_cur[(size_t)k * B + b] = pk;
       if (tok == (int)eos) {                              // Beam.py:112-118
         if (nf == 0 || best[k].v > fin_score[b]) { fin_score[b] = best[k].v; fin_t[b] = step + 1; fin_k[b] = k; }
         ++nf;
@@ -139,15 +149,28 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gpre, const float* __
 
 }  // namespace
 
-extern "C" int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, int64_t eos,
+extern "C" int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, const int64_t* step_dev,
+                                 int64_t* tok_cur, int32_t* prev_cur, int64_t eos,
                                  float* scores, int64_t* next_ys, int32_t* prev_ks, float* fin_score,
                                  int32_t* fin_t, int32_t* fin_k, int32_t* n_fin, int32_t* done,
                                  int32_t* n_active, void* stream) {
   VMMT_REQUIRE(K >= 1 && K <= KMAX, "beam_advance: beam size %d outside [1,%d]", K, KMAX);
-  beam_advance_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logp, B, K, V, step, eos, scores, next_ys,
-                                                          prev_ks, fin_score, fin_t, fin_k, n_fin,
-                                                          done, n_active);
+  beam_advance_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logp, B, K, V, step, step_dev, tok_cur, prev_cur, eos,
+                                                          scores, next_ys, prev_ks, fin_score, fin_t, fin_k,
+                                                          n_fin, done, n_active);
   return vmmt_check_launch("beam_advance");
+}
+
+// hist[step][r][:] = cur[r][:]  (attention rows of the current step into the per-step history)
+__global__ void beam_record_kernel(const float* __restrict__ cur, float* __restrict__ hist,
+                                   const int64_t* __restrict__ step_dev, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) hist[(size_t)*step_dev * n + i] = cur[i];
+}
+
+extern "C" int vmmt_beam_record(const float* cur, float* hist, const int64_t* step_dev, int64_t n, void* stream) {
+  beam_record_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(cur, hist, step_dev, n);
+  return vmmt_check_launch("beam_record");
 }
 
 extern "C" int vmmt_beam_reorder(const float* src, float* dst, const int32_t* prev_k_step,

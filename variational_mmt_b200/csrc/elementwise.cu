@@ -68,13 +68,14 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 
 // column sums of a row-major [M,N] matrix (bias gradients), accumulated into out[N]
 __global__ void colsum_kernel(const float* __restrict__ a, int64_t lda, int M, int N,
-                              float* __restrict__ out, int rows_per_block) {
+                              float* __restrict__ out, float* __restrict__ out2, int rows_per_block) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
   float s = 0.f;
   for (int m = m0; m < m1; ++m) s += a[(size_t)m * lda + n];
-  if (gridDim.y == 1) out[n] += s; else atomicAdd(out + n, s);
+  if (gridDim.y == 1) { out[n] += s; if (out2) out2[n] += s; }
+  else { atomicAdd(out + n, s); if (out2) atomicAdd(out2 + n, s); }
 }
 
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, int64_t n) {
@@ -278,12 +279,12 @@ extern "C" int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t 
   act_bwd_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(dy, y, dx, n, act);
   return vmmt_check_launch("act_bwd");
 }
-extern "C" int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, void* stream) {
+extern "C" int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, float* out2, void* stream) {
   if (M <= 0 || N <= 0) return VMMT_OK;
   int rows = 64;
   dim3 grid(ceil_div(N, 128), ceil_div(M, rows));
   if (grid.y == 1) rows = M;
-  colsum_kernel<<<grid, 128, 0, ST(stream)>>>(a, lda, M, N, out, rows);
+  colsum_kernel<<<grid, 128, 0, ST(stream)>>>(a, lda, M, N, out, out2, rows);
   return vmmt_check_launch("colsum");
 }
 extern "C" int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {

@@ -41,6 +41,16 @@ __host__ __device__ constexpr size_t smem_bytes(int BN, int STAGES) {
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -285,16 +295,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_mark(g.trace, 1);
 
+  // Producer and MMA warps run CONVERGED (all 32 lanes execute the loops, one elected lane issues): descriptor /
+  // coordinate values then stay in uniform registers.  Inside an `if (lane == 0)` region ptxas has to move every
+  // operand of UTMALDG / UTCHMMA into uniform registers with an ELECT + R2UR.BROADCAST loop (~65 cycles per MMA).
+  const bool leader = elect_one();
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const uint32_t fb = full0 + 8 * s;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      const uint32_t fb = full0 + 8 * s;
+      const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
+      const int k = (kb0 + i) * BK;
+      if (leader) {
         mbar_expect_tx(fb, STAGE);
-        const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
-        const int k = (kb0 + i) * BK;
         if (!A_MN) {
           tma_load_2d(sa, &tmA, k, m0, fb);                        // box {32 k, 128 rows}
         } else {
@@ -308,30 +322,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, n0 + 32 * j, k, fb);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
-        if (i == 0) trace_mark(g.trace, 2);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
+    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                           ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      if (i == 0 && lane == 0) trace_mark(g.trace, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
 #pragma unroll
-        for (int j = 0; j < BK / UMMA_K; ++j) {
-          const uint64_t ad = A_MN ? make_desc(sa + j * 1024, BK * 128, 512, 1) : make_desc(sa + j * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_desc(sb + j * 1024, BK * 128, 512, 1) : make_desc(sb + j * 32, 16, 1024);
-          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
-        }
-        umma_commit(empty0 + 8 * s);          // slot reusable once these MMAs have read it
+      for (int j = 0; j < BK / UMMA_K; ++j) {
+        const uint64_t ad = A_MN ? make_desc(sa + j * 1024, BK * 128, 512, 1) : make_desc(sa + j * 32, 16, 1024);
+        const uint64_t bd = B_MN ? make_desc(sb + j * 1024, BK * 128, 512, 1) : make_desc(sb + j * 32, 16, 1024);
+        if (leader) umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
       }
-      umma_commit(tfull);                      // accumulator complete
-      trace_mark(g.trace, 3);
+      if (leader) umma_commit(empty0 + 8 * s);          // slot reusable once these MMAs have read it
+      __syncwarp();
     }
+    if (leader) umma_commit(tfull);                      // accumulator complete
+    if (lane == 0) trace_mark(g.trace, 3);
   } else {
     // ---------------- epilogue warps: TMEM lane quarter = warp % 4
     const int q = warp & 3;

@@ -140,7 +140,7 @@ extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const floa
   // dW[V,H] += dl^T[V,M] x[M,H]
   rc = vmmt_gemm(dl, V, 0, x, H, 0, dW, H, V, H, M, nullptr, VMMT_ACT_NONE, 1, stream);
   if (rc) return rc;
-  return vmmt_colsum_acc(dl, V, M, V, db, stream);
+  return vmmt_colsum_acc(dl, V, M, V, db, nullptr, stream);
 }
 
 extern "C" int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H,

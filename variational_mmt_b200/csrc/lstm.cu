@@ -405,13 +405,12 @@ constexpr size_t CTR_BYTES = 256;    // counters live at the head of the workspa
 }  // namespace
 
 extern "C" size_t vmmt_lstm_workspace_bytes(int ndir, int N, int H) {
-  return CTR_BYTES + (size_t)ndir * 2 * N * H * sizeof(float);
+  return CTR_BYTES + vmmt_lstm_step_workspace_floats(ndir, N, H) * sizeof(float);
 }
 
 extern "C" int vmmt_lstm_seq_supported(int ndir, int N, int H) {
-  Plan p;
-  return (ndir >= 1 && ndir <= 2 && make_plan(false, ndir, N, H, &p) == VMMT_OK &&
-          make_plan(true, ndir, N, H, &p) == VMMT_OK) ? 1 : 0;
+  (void)N; (void)H;                       // any shape: cluster / persistent kernels, else the step-wise GEMM path
+  return (ndir >= 1 && ndir <= 2) ? 1 : 0;
 }
 
 extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T,
@@ -420,15 +419,18 @@ extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_fwd: ndir must be 1 or 2 (got %d)", ndir);
   VMMT_REQUIRE(T > 0 && N > 0 && H > 0, "lstm_seq_fwd: bad dims T=%d N=%d H=%d", T, N, H);
   // tensor-core cluster path (default); VMMT_GEMM=simt / vmmt_set_gemm_mode(1) selects the exact-fp32 SIMT kernels
-  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && vmmt_lstm_tc_supported(ndir, N, H))
+  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_STEPWISE") &&
+      vmmt_lstm_tc_supported(ndir, N, H))
     return vmmt_lstm_tc_fwd(dirs, ndir, lengths, T, N, H, (cudaStream_t)stream);
-  Plan p;
-  VMMT_REQUIRE(make_plan(false, ndir, N, H, &p) == VMMT_OK,
-               "lstm_seq_fwd: N=%d H=%d does not fit the persistent kernel", N, H);
   if (workspace_bytes < vmmt_lstm_workspace_bytes(ndir, N, H)) {
     vmmt_set_error("lstm_seq_fwd: workspace too small");
     return VMMT_EWORKSPACE;
   }
+  Plan p;
+  // large batch / hidden size: one GEMM + one cell kernel per step (lstm_step.cu)
+  if (getenv("VMMT_LSTM_STEPWISE") || make_plan(false, ndir, N, H, &p) != VMMT_OK)
+    return vmmt_lstm_step_fwd(dirs, ndir, lengths, T, N, H,
+                              reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + CTR_BYTES), (cudaStream_t)stream);
   cudaStream_t s = (cudaStream_t)stream;
   VMMT_CUDA(cudaMemsetAsync(workspace, 0, CTR_BYTES, s));
   FwdParams P;
@@ -449,15 +451,16 @@ extern "C" int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int
                                  int T, int N, int H, void* workspace, size_t workspace_bytes, void* stream) {
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_bwd: ndir must be 1 or 2 (got %d)", ndir);
   if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_SIMT_BWD") &&
-      vmmt_lstm_tc_supported(ndir, N, H))
+      !getenv("VMMT_LSTM_STEPWISE") && vmmt_lstm_tc_supported(ndir, N, H))
     return vmmt_lstm_tc_bwd(dirs, ndir, lengths, T, N, H, (cudaStream_t)stream);
-  Plan p;
-  VMMT_REQUIRE(make_plan(true, ndir, N, H, &p) == VMMT_OK,
-               "lstm_seq_bwd: N=%d H=%d does not fit the persistent kernel", N, H);
-  if (workspace_bytes < CTR_BYTES) {
+  if (workspace_bytes < vmmt_lstm_workspace_bytes(ndir, N, H)) {
     vmmt_set_error("lstm_seq_bwd: workspace too small");
     return VMMT_EWORKSPACE;
   }
+  Plan p;
+  if (getenv("VMMT_LSTM_STEPWISE") || make_plan(true, ndir, N, H, &p) != VMMT_OK)
+    return vmmt_lstm_step_bwd(dirs, ndir, lengths, T, N, H,
+                              reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + CTR_BYTES), (cudaStream_t)stream);
   cudaStream_t s = (cudaStream_t)stream;
   VMMT_CUDA(cudaMemsetAsync(workspace, 0, CTR_BYTES, s));
   BwdParams P;

@@ -89,8 +89,8 @@ def gemm(a, b, out, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NO
     return out
 
 
-def colsum_acc(a, M, N, out):
-    L.call("vmmt_colsum_acc", fptr(a), a.stride(0), M, N, fptr(out), stream())
+def colsum_acc(a, M, N, out, out2=None):
+    L.call("vmmt_colsum_acc", fptr(a), a.stride(0), M, N, fptr(out), fptr(out2), stream())
 
 
 # --------------------------------------------------------------------------------------------
@@ -283,10 +283,10 @@ class LSTMLayerFn(Function):
                 t0 = 0 if d == 0 else T - 1
                 gemm(dg[d][t0], h0[d], grad_buf(w_hh), 4 * Hd, Hd, N, a_kmajor=False, b_kmajor=False,
                      accumulate=1)
-            if b_ih.requires_grad:
-                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih))
-            if b_hh.requires_grad:
-                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_hh))
+            if b_ih.requires_grad and b_hh.requires_grad:              # identical sums: one pass, two outputs
+                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih), grad_buf(b_hh))
+            elif b_ih.requires_grad or b_hh.requires_grad:
+                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih if b_ih.requires_grad else b_hh))
         if rowbias is not None and ctx.needs_input_grad[4]:
             drow = torch.zeros(N, 4 * Hd, device=dev, dtype=torch.float32)
             for d in range(ndir):                                      # the term enters every direction

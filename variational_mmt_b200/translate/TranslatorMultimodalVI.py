@@ -14,6 +14,8 @@ The decoder step itself (1-step LSTM x 2 layers + attention + generator) calls t
 (no autograd bookkeeping): GEMMs for the gate pre-activations (M = K*B rows), the fused cell kernel, the
 attention core, the log-softmax generator.
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -22,6 +24,10 @@ from .. import ops
 from .._lib import ACT_NONE, ACT_TANH, fptr, ptr, stream
 
 PAD_WORD, BOS_WORD, EOS_WORD = "<blank>", "<s>", "</s>"
+
+
+class _State(object):
+    """Device buffers of one decode bucket (all at fixed addresses: the step graph refers to them)."""
 
 
 class TranslatorMultimodalVI(object):
@@ -43,10 +49,122 @@ class TranslatorMultimodalVI(object):
         self.test_img_feats, self.multimodal_model_type = test_img_feats, multimodal_model_type
         self.beam_accum = None
         self.poll_every = 4            # steps between host polls of the active-sentence counter
+        self.use_graph = True          # replay the decode step from a CUDA graph (one per (sentences, src_len) bucket)
+        self.return_attention = True   # copy the per-step attention history back for ret["attention"]
+        self.max_buckets = 8
+        self._buckets = collections.OrderedDict()
         vocab = fields["tgt"].vocab
         self.pad, self.bos, self.eos = vocab.stoi[PAD_WORD], vocab.stoi[BOS_WORD], vocab.stoi[EOS_WORD]
 
     # ------------------------------------------------------------------------------------------
+    def _buffers(self, B, S, dev):
+        """Static device buffers (and the captured step graph) of one (sentences, src_len) bucket."""
+        key = (B, S, str(dev))
+        st = self._buckets.get(key)
+        if st is not None:
+            self._buckets.move_to_end(key)
+            return st
+        while len(self._buckets) >= self.max_buckets:
+            self._buckets.popitem(last=False)
+        model, dec = self.model, self.model.decoder
+        K, H, nl, Lmax = self.beam_size, dec.hidden_size, dec.num_layers, self.max_length
+        R = K * B
+        E = dec.embeddings.embedding_size
+        V = model.generator[0].weight.size(0)
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        st = _State()
+        st.B, st.S, st.R = B, S, R
+        st.ctx = torch.zeros(S, R, H, **f32)
+        st.len_r = torch.zeros(R, device=dev, dtype=torch.int64)
+        st.zb = torch.zeros(R, 4 * H, **f32)
+        st.h, st.c = torch.zeros(nl, R, H, **f32), torch.zeros(nl, R, H, **f32)
+        st.h2, st.c2 = torch.zeros_like(st.h), torch.zeros_like(st.c)
+        st.scores = torch.zeros(B, K, **f32)
+        st.next_ys = torch.zeros(Lmax + 1, K, B, device=dev, dtype=torch.int64)
+        st.prev_ks = torch.zeros(Lmax, K, B, **i32)
+        st.tok_cur = torch.zeros(K, B, device=dev, dtype=torch.int64)
+        st.prev_cur = torch.zeros(K, B, **i32)
+        st.fin_score = torch.zeros(B, **f32)
+        st.fin_t, st.fin_k, st.n_fin, st.done = (torch.zeros(B, **i32) for _ in range(4))
+        st.n_active = torch.zeros(1, **i32)
+        st.step = torch.zeros(1, device=dev, dtype=torch.int64)
+        st.attn_hist = torch.zeros(Lmax, R, S, **f32)
+        st.align = torch.zeros(R, S, **f32)
+        st.emb, st.gpre = torch.zeros(R, E, **f32), torch.zeros(R, 4 * H, **f32)
+        st.qp, st.cvec, st.out = (torch.zeros(R, H, **f32) for _ in range(3))
+        st.logp, st.lse = torch.zeros(R, V, **f32), torch.zeros(R, **f32)
+        st.graph = None
+        st.att_host = None
+        self._buckets[key] = st
+        return st
+
+    def _reset(self, st):
+        st.scores.zero_()
+        st.next_ys.fill_(self.pad)
+        st.next_ys[0, 0] = self.bos
+        st.tok_cur.copy_(st.next_ys[0])
+        st.prev_ks.zero_()
+        st.prev_cur.zero_()
+        st.fin_score.zero_()
+        for t in (st.fin_t, st.fin_k, st.n_fin, st.done, st.step):
+            t.zero_()
+        st.n_active.fill_(st.B)
+
+    def _issue_step(self, st):
+        """One decode position for all K*B rows; every argument is a fixed device address (the step index is
+        device-resident), so the same launch sequence is valid for every step and can be replayed from a graph."""
+        model, dec = self.model, self.model.decoder
+        K, B, R, S = self.beam_size, st.B, st.R, st.S
+        H, nl = dec.hidden_size, dec.num_layers
+        E = dec.embeddings.embedding_size
+        w, gen = dec.rnn, model.generator[0]
+        V = gen.weight.size(0)
+        sm = stream()
+        L.call("vmmt_embedding_fwd", ptr(st.tok_cur), R, fptr(dec.embeddings.word_lut.weight), E, fptr(st.emb), sm)
+        x = st.emb
+        for l in range(nl):
+            w_ih, w_hh = getattr(w, "weight_ih_l%d" % l), getattr(w, "weight_hh_l%d" % l)
+            in_dim = E if l == 0 else H
+            ops.gemm(x, w_ih[:, :in_dim], st.gpre, R, 4 * H, in_dim)
+            ops.gemm(st.h[l], w_hh, st.gpre, R, 4 * H, H, accumulate=1)
+            L.call("vmmt_lstm_cell_fwd", fptr(st.gpre), fptr(getattr(w, "bias_ih_l%d" % l)),
+                   fptr(getattr(w, "bias_hh_l%d" % l)), fptr(st.zb) if l == 0 else None, fptr(st.c[l]),
+                   fptr(st.h2[l]), fptr(st.c2[l]), R, H, sm)
+            x = st.h2[l]
+        # attention, one step (GlobalAttention.py:147-151,169-190)
+        if dec.attn.attn_type == "general":
+            ops.gemm(x, dec.attn.linear_in.weight, st.qp, R, H, H)
+            q = st.qp
+        else:
+            q = x
+        L.call("vmmt_attention_fwd", fptr(q), fptr(st.ctx), ptr(st.len_r), fptr(st.align), fptr(st.cvec), 1, R, S, H, sm)
+        L.call("vmmt_beam_record", fptr(st.align), fptr(st.attn_hist), ptr(st.step), R * S, sm)
+        w_out = dec.attn.linear_out.weight
+        ops.gemm(st.cvec, w_out[:, :H], st.out, R, H, H)
+        ops.gemm(x, w_out[:, H:], st.out, R, H, H, act=ACT_TANH, accumulate=2)
+        L.call("vmmt_generator_logprobs", fptr(st.out), fptr(gen.weight), fptr(gen.bias), R, H, V, fptr(st.logp),
+               fptr(st.lse), sm)
+        # Beam.advance for every sentence + DecoderState.beam_update (Beam.py:64-123, Models.py:589-594)
+        L.call("vmmt_beam_advance", fptr(st.logp), B, K, V, 0, ptr(st.step), ptr(st.tok_cur), ptr(st.prev_cur),
+               self.eos, fptr(st.scores), ptr(st.next_ys), ptr(st.prev_ks), fptr(st.fin_score), ptr(st.fin_t),
+               ptr(st.fin_k), ptr(st.n_fin), ptr(st.done), ptr(st.n_active), sm)
+        L.call("vmmt_beam_reorder", fptr(st.h2), fptr(st.h), ptr(st.prev_cur), ptr(st.done), nl, K, B, H, sm)
+        L.call("vmmt_beam_reorder", fptr(st.c2), fptr(st.c), ptr(st.prev_cur), ptr(st.done), nl, K, B, H, sm)
+        L.call("vmmt_counter_add", ptr(st.step), 1, sm)
+
+    def _capture(self, st):
+        dev = st.ctx.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                  # lazy one-time work must not happen inside the capture
+            self._issue_step(st)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._issue_step(st)
+        st.graph = g
+
     @torch.no_grad()
     def translate_batch(self, batch, data=None, sent_idx=None):
         model = self.model
@@ -56,113 +174,77 @@ class TranslatorMultimodalVI(object):
         if src.dim() == 2:
             src = src.unsqueeze(2)
         dev = next(model.parameters()).device
-        src, src_lengths = src.to(dev), src_lengths.to(dev)
+        src, src_lengths = src.to(dev, non_blocking=True), src_lengths.to(dev, non_blocking=True)
         S, B = src.size(0), src.size(1)
         K = self.beam_size
-        R = K * B
         H = dec.hidden_size
-        nl = dec.num_layers
+        st = self._buffers(B, S, dev)
+        R = st.R
+        if self.use_graph and st.graph is None:       # capture on the zero-filled bucket, before real data goes in
+            self._reset(st)
+            self._capture(st)
         # (1) encoder + prior mean (TranslatorMultimodalVI.py:125-138)
         enc_states, context = model.encoder(src, src_lengths)
         net = model.gen_net_global if model.conditional else model.inf_net_global
         q0, _ = net(context, src_lengths)
         z = q0.mean()                                                     # [B, Z]
-        # (2) beam-major tiling (:146-158)
-        ctx_r = context.repeat(1, K, 1).contiguous()                      # [S, K*B, H]
-        len_r = src_lengths.repeat(K).contiguous()
-        h = dec._fix_enc_hidden(enc_states[0]).repeat(1, K, 1).contiguous()   # [L, K*B, H]
-        c = dec._fix_enc_hidden(enc_states[1]).repeat(1, K, 1).contiguous()
-        h2, c2 = torch.empty_like(h), torch.empty_like(c)
+        # (2) beam-major tiling (:146-158) into the bucket's static buffers
+        st.ctx.view(S, K, B, H).copy_(context.unsqueeze(1).expand(S, K, B, H))
+        st.len_r.view(K, B).copy_(src_lengths.unsqueeze(0).expand(K, B))
+        h0, c0 = dec._fix_enc_hidden(enc_states[0]), dec._fix_enc_hidden(enc_states[1])
+        nl = h0.size(0)
+        st.h.view(nl, K, B, H).copy_(h0.unsqueeze(1).expand(nl, K, B, H))
+        st.c.view(nl, K, B, H).copy_(c0.unsqueeze(1).expand(nl, K, B, H))
         E = dec.embeddings.embedding_size
-        w = dec.rnn
         zb = torch.empty(B, 4 * H, device=dev)
-        ops.gemm(z.contiguous(), w.weight_ih_l0[:, E:], zb, B, 4 * H, z.size(1))   # z W_ih[:, E:]^T once per batch
-        zb = zb.repeat(K, 1).contiguous()
+        ops.gemm(z.contiguous(), dec.rnn.weight_ih_l0[:, E:], zb, B, 4 * H, z.size(1))   # z W_ih[:, E:]^T once per batch
+        st.zb.view(K, B, 4 * H).copy_(zb.unsqueeze(0).expand(K, B, 4 * H))
+        self._reset(st)
         Lmax = self.max_length
-        f32 = dict(device=dev, dtype=torch.float32)
-        scores = torch.zeros(B, K, **f32)
-        next_ys = torch.full((Lmax + 1, K, B), self.pad, device=dev, dtype=torch.int64)
-        next_ys[0, 0] = self.bos
-        prev_ks = torch.zeros(Lmax, K, B, device=dev, dtype=torch.int32)
-        fin_score = torch.zeros(B, **f32)
-        fin_t = torch.zeros(B, device=dev, dtype=torch.int32)
-        fin_k = torch.zeros(B, device=dev, dtype=torch.int32)
-        n_fin = torch.zeros(B, device=dev, dtype=torch.int32)
-        done = torch.zeros(B, device=dev, dtype=torch.int32)
-        n_active = torch.full((1,), B, device=dev, dtype=torch.int32)
-        attn_hist = torch.zeros(Lmax, R, S, **f32)
-        emb_w = dec.embeddings.word_lut.weight
-        gen = model.generator[0]
-        V = gen.weight.size(0)
-        emb = torch.empty(R, E, **f32)
-        gpre = torch.empty(R, 4 * H, **f32)
-        qp = torch.empty(R, H, **f32)
-        cvec = torch.empty(R, H, **f32)
-        out = torch.empty(R, H, **f32)
-        logp = torch.empty(R, V, **f32)
-        lse = torch.empty(R, **f32)
-        w_in = dec.attn.linear_in.weight if dec.attn.attn_type == "general" else None
-        w_out = dec.attn.linear_out.weight
-        st = stream()
         steps = 0
         # (3) the step loop (:163-218)
         for i in range(Lmax):
-            if i % self.poll_every == 0 and i > 0 and int(n_active.item()) == 0:
+            if i % self.poll_every == 0 and i > 0 and int(st.n_active.item()) == 0:
                 break
-            tok = next_ys[i].view(R)
-            L.call("vmmt_embedding_fwd", ptr(tok), R, fptr(emb_w), E, fptr(emb), st)
-            x = emb
-            for l in range(nl):
-                w_ih = getattr(w, "weight_ih_l%d" % l)
-                w_hh = getattr(w, "weight_hh_l%d" % l)
-                in_dim = E if l == 0 else H
-                ops.gemm(x, w_ih[:, :in_dim], gpre, R, 4 * H, in_dim)
-                ops.gemm(h[l], w_hh, gpre, R, 4 * H, H, accumulate=1)
-                L.call("vmmt_lstm_cell_fwd", fptr(gpre), fptr(getattr(w, "bias_ih_l%d" % l)),
-                       fptr(getattr(w, "bias_hh_l%d" % l)), fptr(zb) if l == 0 else None, fptr(c[l]),
-                       fptr(h2[l]), fptr(c2[l]), R, H, st)
-                x = h2[l]
-            # attention, one step (GlobalAttention.py:147-151,169-190)
-            if w_in is not None:
-                ops.gemm(x, w_in, qp, R, H, H)
-                q = qp
+            if st.graph is not None:
+                st.graph.replay()
             else:
-                q = x
-            align = attn_hist[i]
-            L.call("vmmt_attention_fwd", fptr(q), fptr(ctx_r), ptr(len_r), fptr(align), fptr(cvec), 1, R, S, H, st)
-            ops.gemm(cvec, w_out[:, :H], out, R, H, H)
-            ops.gemm(x, w_out[:, H:], out, R, H, H, act=ACT_TANH, accumulate=2)
-            L.call("vmmt_generator_logprobs", fptr(out), fptr(gen.weight), fptr(gen.bias), R, H, V, fptr(logp),
-                   fptr(lse), st)
-            # Beam.advance for every sentence + DecoderState.beam_update (Beam.py:64-123, Models.py:589-594)
-            L.call("vmmt_beam_advance", fptr(logp), B, K, V, i, self.eos, fptr(scores), ptr(next_ys), ptr(prev_ks),
-                   fptr(fin_score), ptr(fin_t), ptr(fin_k), ptr(n_fin), ptr(done), ptr(n_active), st)
-            L.call("vmmt_beam_reorder", fptr(h2), fptr(h), ptr(prev_ks[i]), ptr(done), nl, K, B, H, st)
-            L.call("vmmt_beam_reorder", fptr(c2), fptr(c), ptr(prev_ks[i]), ptr(done), nl, K, B, H, st)
+                self._issue_step(st)
             steps = i + 1
-        # (4) hypotheses (Beam.sort_finished / get_hyp, Beam.py:128-153; _from_beam :228-243)
-        ys = next_ys[: steps + 1].cpu().numpy()
-        pk = prev_ks[:steps].cpu().numpy()
-        fs, ft, fk, nf = fin_score.cpu().numpy(), fin_t.cpu().numpy(), fin_k.cpu().numpy(), n_fin.cpu().numpy()
-        sc = scores.cpu().numpy()
-        dn = done.cpu().numpy()
+        # (4) hypotheses (Beam.sort_finished / get_hyp, Beam.py:128-153; _from_beam :228-243): back-pointer walk for
+        # all sentences at once (one vectorised pass per step instead of one Python iteration per token)
+        ys = st.next_ys[: steps + 1].cpu().numpy()
+        pk = st.prev_ks[:steps].cpu().numpy()
+        fs, ft, fk, nf = st.fin_score.cpu().numpy(), st.fin_t.cpu().numpy(), st.fin_k.cpu().numpy(), st.n_fin.cpu().numpy()
+        sc = st.scores.cpu().numpy()
         lens = src_lengths.cpu().numpy()
-        att = attn_hist[:steps].view(steps, K, B, S).cpu()
-        # a sentence that was frozen (done) stopped advancing at its own last step
+        att = None
+        if self.return_attention:
+            if st.att_host is None:
+                st.att_host = torch.empty(st.attn_hist.shape, dtype=torch.float32, pin_memory=True)
+            st.att_host[:steps].copy_(st.attn_hist[:steps], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            att = st.att_host[:steps].view(steps, K, B, S).numpy()
+        fin = nf >= 1                                    # else sort_finished(minimum=n_best): top of the beam as it stands
+        t_end = np.where(fin, ft, steps).astype(np.int64)
+        k = np.where(fin, fk, 0).astype(np.int64)
+        score = np.where(fin, fs, sc[:, 0])
+        rows = np.arange(B)
+        toks = np.full((B, max(steps, 1)), self.pad, np.int64)
+        best_att = np.zeros((B, max(steps, 1), S), np.float32) if att is not None else None
+        for j in range(steps - 1, -1, -1):
+            live = j < t_end
+            toks[live, j] = ys[j + 1, k[live], rows[live]]
+            k = np.where(live, pk[j, k, rows], k)        # attn[j] was re-ordered by prev_ks[j] (Beam.py:107)
+            if best_att is not None:
+                best_att[live, j] = att[j, k[live], rows[live]]
         ret = {"predictions": [], "scores": [], "attention": []}
         for b in range(B):
-            if nf[b] >= 1:
-                score, t, k = float(fs[b]), int(ft[b]), int(fk[b])
-            else:                                        # sort_finished(minimum=n_best): top of the beam as it stands
-                score, t, k = float(sc[b, 0]), steps, 0
-            hyp, rows = [], []
-            for j in range(t - 1, -1, -1):
-                hyp.append(int(ys[j + 1, k, b]))
-                k = int(pk[j, k, b])                     # attn[j] was re-ordered by prev_ks[j] (Beam.py:107)
-                rows.append(att[j, k, b, : int(lens[b])])
-            ret["predictions"].append([hyp[::-1]])
-            ret["scores"].append([score])
-            ret["attention"].append([torch.stack(rows[::-1]) if rows else torch.zeros(0, int(lens[b]))])
+            n = int(t_end[b])
+            ret["predictions"].append([toks[b, :n].tolist()])
+            ret["scores"].append([float(score[b])])
+            ret["attention"].append([torch.from_numpy(best_att[b, :n, : int(lens[b])].copy()) if best_att is not None
+                                     else torch.zeros(0, int(lens[b]))])
         ret["gold_score"] = [0] * B
         ret["batch"] = batch
         ret["steps"] = steps
