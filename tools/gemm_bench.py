@@ -6,7 +6,8 @@ import torch
 from variational_mmt_b200 import ops, _lib
 torch.backends.cuda.matmul.allow_tf32 = True
 dev = "cuda"
-shapes = [(1240, 2000, 500, 1, 1), (1240, 10000, 500, 1, 1), (1240, 500, 10000, 1, 0), (10000, 500, 1240, 0, 0),
+shapes = [(40, 500, 500, 1, 0), (500, 500, 40, 0, 0), (1000, 250, 1248, 0, 0), (40, 500, 3048, 1, 1), (2048, 2048, 40, 0, 0), (40, 2048, 2048, 1, 1), (1280, 1000, 500, 1, 1), (2000, 500, 1200, 0, 0),
+          (1240, 2000, 500, 1, 1), (1240, 10000, 500, 1, 1), (1240, 500, 10000, 1, 0), (10000, 500, 1240, 0, 0),
           (2000, 500, 1240, 0, 0), (1240, 500, 2000, 1, 0), (4096, 4096, 4096, 1, 1), (8192, 8192, 1024, 1, 1),
           (40448, 32000, 1024, 1, 1)]
 flush = torch.empty(64 << 20, device=dev)

@@ -8,7 +8,7 @@ import torch
 from . import _lib as L
 from ._lib import fptr, stream
 from .flat import flatten_parameters
-from . import distributed
+from . import distributed, ops
 
 
 class _ParamList(torch.nn.Module):
@@ -58,6 +58,7 @@ class Optim(object):
 
     def step(self):
         self._step += 1
+        ops.join_side()
         if self.decay_method == "noam":
             self._set_rate(self.original_lr * (self.model_size ** (-0.5) *
                            min(self._step ** (-0.5), self._step * self.warmup_steps ** (-1.5))))

@@ -193,5 +193,6 @@ class NMTVIModel1LossCompute(nn.Module):
         state["target"] = state["target"][:shard_size]
         loss, stats = self._compute_loss(batch, **state)
         loss.div(normalization).backward()
+        ops.join_side()                 # weight-gradient GEMMs issued on the side stream are complete from here on
         batch_stats.update(stats)
         return batch_stats

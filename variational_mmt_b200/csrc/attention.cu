@@ -9,6 +9,7 @@
 // Everything is time-major, exactly as the decoder holds it, so the reference's two transposing
 // copies (GlobalAttention.py:204-205) disappear.  One warp per query (t,b); the context rows of
 // one batch element stay L1/L2 resident across the queries of that element.
+#include <stdlib.h>
 #include "common.cuh"
 #include "vmmt_internal.h"
 
@@ -180,6 +181,231 @@ __global__ void attn_bwd_ctx_kernel(const float* __restrict__ dc, const float* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled kernels (used whenever T > 1): one CTA per (batch element, tile of 16 queries).  The two contractions of the
+// attention core are tiny batched GEMMs ([16,H] x [H,S] and [16,S] x [S,H]); the one-warp-per-query kernels above
+// re-read the whole context of a batch element once per query and are latency bound.  Here the context chunk is
+// staged through shared memory once per 16 queries, scores / weights never leave registers + shared memory, and
+// every global access is a coalesced 128-byte row segment.
+constexpr int TT = 16;             // queries per CTA
+constexpr int KC = 32;             // contraction chunk staged in shared memory
+constexpr int TILE_THREADS = 256;
+
+// P[tt][j] = sum_k X[(t0+tt), b, k] * ctx[j, b, k];  thread (ty = warp, tx = lane) holds tt = 2 ty + {0,1}, j = tx + 32 jj.
+// The next k-chunk is fetched into registers while the current one is being contracted (one global-latency
+// exposure per kernel instead of one per chunk).
+__device__ __forceinline__ void qk_tile(const float* __restrict__ X, const float* __restrict__ ctx, int t0, int T, int b,
+                                        int B, int S, int H, float (*Xs)[KC + 1], float (*Cs)[KC + 1], float (&acc)[2][4]) {
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  constexpr int XP = TT * KC / TILE_THREADS;           // 2 staged X elements per thread
+  constexpr int CP = SMAX * KC / TILE_THREADS;         // up to 16 staged context elements per thread
+  const int srows = ((S + 31) / 32) * 32;
+  const int cp_used = srows * KC / TILE_THREADS;       // 4 per 32 source positions
+  float xr[XP], cr[CP];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < XP; ++i) {
+      const int e = tid + i * TILE_THREADS, r = e / KC, k = k0 + (e % KC), t = t0 + r;
+      xr[i] = (t < T && k < H) ? __ldg(X + ((size_t)t * B + b) * H + k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < CP; ++i) {
+      if (i < cp_used) {
+        const int e = tid + i * TILE_THREADS, j = e / KC, k = k0 + (e % KC);
+        cr[i] = (j < S && k < H) ? __ldg(ctx + ((size_t)j * B + b) * H + k) : 0.f;
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.f;
+  fetch(0);
+  for (int k0 = 0; k0 < H; k0 += KC) {
+    __syncthreads();                                   // previous chunk fully consumed
+#pragma unroll
+    for (int i = 0; i < XP; ++i) { const int e = tid + i * TILE_THREADS; Xs[e / KC][e % KC] = xr[i]; }
+#pragma unroll
+    for (int i = 0; i < CP; ++i)
+      if (i < cp_used) { const int e = tid + i * TILE_THREADS; Cs[e / KC][e % KC] = cr[i]; }
+    __syncthreads();
+    if (k0 + KC < H) fetch(k0 + KC);                   // in flight during the contraction below
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const float x0 = Xs[2 * ty][k], x1 = Xs[2 * ty + 1][k];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        if (32 * jj < S) {                             // uniform: skip the 32-position groups beyond the source length
+          const float c = Cs[tx + 32 * jj][k];
+          acc[0][jj] = fmaf(x0, c, acc[0][jj]);
+          acc[1][jj] = fmaf(x1, c, acc[1][jj]);
+        }
+      }
+    }
+  }
+}
+
+// O[(t0+tt), b, k] = sum_{j<len} W[j][tt] * ctx[j, b, k];  W is the [SMAX][TT] shared-memory tile (tt fastest)
+__device__ __forceinline__ void wv_tile(const float (*Ws)[TT], const float* __restrict__ ctx, float* __restrict__ O,
+                                        int t0, int T, int b, int B, int len, int H) {
+  for (int k = threadIdx.x; k < H; k += TILE_THREADS) {
+    float acc[TT];
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc[i] = 0.f;
+    for (int j0 = 0; j0 < len; j0 += 8) {
+      float c8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)                        // 8 independent loads in flight; weights beyond len are 0
+        c8[u] = (j0 + u < len) ? __ldg(ctx + ((size_t)(j0 + u) * B + b) * H + k) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j0 + u < len) {
+          const float c = c8[u];
+          const float4* w4 = reinterpret_cast<const float4*>(Ws[j0 + u]);
+#pragma unroll
+          for (int q = 0; q < TT / 4; ++q) {
+            const float4 w = w4[q];
+            acc[4 * q] = fmaf(w.x, c, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, c, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w.z, c, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, c, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TT; ++i)
+      if (t0 + i < T) O[((size_t)(t0 + i) * B + b) * H + k] = acc[i];
+  }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+attn_fwd_tiled_kernel(const float* __restrict__ qp, const float* __restrict__ ctx, const int64_t* __restrict__ lengths,
+                      float* __restrict__ align, float* __restrict__ cvec, int T, int B, int S, int H, int ntile) {
+  __shared__ float Xs[TT][KC + 1];
+  __shared__ float Cs[SMAX][KC + 1];
+  __shared__ __align__(16) float Ws[SMAX][TT];
+  const int b = blockIdx.x / ntile, t0 = (blockIdx.x % ntile) * TT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int len = lengths ? min((int)lengths[b], S) : S;
+  float acc[2][4];
+  qk_tile(qp, ctx, t0, T, b, B, S, H, Xs, Cs, acc);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int tt = 2 * ty + i, t = t0 + tt;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      if (tx + 32 * jj >= len) acc[i][jj] = -INFINITY;
+      mx = fmaxf(mx, acc[i][jj]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) { acc[i][jj] = expf(acc[i][jj] - mx); sum += acc[i][jj]; }   // exp(-inf) = 0
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = tx + 32 * jj;
+      const float a = acc[i][jj] * inv;
+      Ws[j][tt] = a;
+      if (t < T && j < S) align[((size_t)t * B + b) * S + j] = a;
+    }
+  }
+  __syncthreads();
+  wv_tile(Ws, ctx, cvec, t0, T, b, B, len, H);
+}
+
+// backward, stage 1 per (b, query tile): da = dc ctx^T;  ds = a (da - sum a da) -> dscore;  dqp = ds ctx
+__global__ void __launch_bounds__(TILE_THREADS)
+attn_bwd_query_tiled_kernel(const float* __restrict__ dc, const float* __restrict__ ctx, const float* __restrict__ align,
+                            const int64_t* __restrict__ lengths, float* __restrict__ dscore, float* __restrict__ dqp,
+                            int T, int B, int S, int H, int ntile) {
+  __shared__ float Xs[TT][KC + 1];
+  __shared__ float Cs[SMAX][KC + 1];
+  __shared__ __align__(16) float Ws[SMAX][TT];
+  const int b = blockIdx.x / ntile, t0 = (blockIdx.x % ntile) * TT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int len = lengths ? min((int)lengths[b], S) : S;
+  float da[2][4];
+  qk_tile(dc, ctx, t0, T, b, B, S, H, Xs, Cs, da);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int tt = 2 * ty + i, t = t0 + tt;
+    float a[4], dot = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = tx + 32 * jj;
+      a[jj] = (t < T && j < len) ? align[((size_t)t * B + b) * S + j] : 0.f;
+      dot = fmaf(a[jj], da[i][jj], dot);
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = tx + 32 * jj;
+      const float ds = a[jj] * (da[i][jj] - dot);
+      Ws[j][tt] = ds;
+      if (t < T && j < S) dscore[((size_t)t * B + b) * S + j] = ds;
+    }
+  }
+  __syncthreads();
+  wv_tile(Ws, ctx, dqp, t0, T, b, B, len, H);
+}
+
+// backward, stage 2 per (b, 64 hidden units): dctx[j,b,k] (+)= sum_t ( a[t,b,j] dc[t,b,k] + ds[t,b,j] qp[t,b,k] )
+// thread (k = k0 + tid % 64, jg = tid / 64) owns the contiguous block of JB source positions jg*JB .. jg*JB+JB-1
+__global__ void __launch_bounds__(TILE_THREADS)
+attn_bwd_ctx_tiled_kernel(const float* __restrict__ dc, const float* __restrict__ qp, const float* __restrict__ align,
+                          const float* __restrict__ dscore, float* __restrict__ dctx, int T, int B, int S, int H,
+                          int accumulate, int nk) {
+  __shared__ __align__(16) float As[TT][SMAX];
+  __shared__ __align__(16) float Ds[TT][SMAX];
+  const int b = blockIdx.x / nk, k = (blockIdx.x % nk) * 64 + (threadIdx.x & 63);
+  const int jg = threadIdx.x >> 6;
+  constexpr int JB = SMAX / 4;                       // 32 positions per thread group (covers S <= 128)
+  float acc[JB];
+#pragma unroll
+  for (int i = 0; i < JB; ++i) acc[i] = 0.f;
+  const int jb_used = min(JB, max(0, S - jg * JB));  // positions of this group that exist
+  for (int t0 = 0; t0 < T; t0 += TT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TT * SMAX; e += TILE_THREADS) {
+      const int tt = e / SMAX, j = e % SMAX, t = t0 + tt;
+      const bool ok = t < T && j < S;
+      As[tt][j] = ok ? align[((size_t)t * B + b) * S + j] : 0.f;
+      Ds[tt][j] = ok ? dscore[((size_t)t * B + b) * S + j] : 0.f;
+    }
+    __syncthreads();
+    const int tn = min(TT, T - t0);
+    for (int tt = 0; tt < tn; ++tt) {
+      const size_t row = ((size_t)(t0 + tt) * B + b) * H;
+      const float dcv = k < H ? __ldg(dc + row + k) : 0.f, qv = k < H ? __ldg(qp + row + k) : 0.f;
+      const float4* a4 = reinterpret_cast<const float4*>(&As[tt][jg * JB]);
+      const float4* d4 = reinterpret_cast<const float4*>(&Ds[tt][jg * JB]);
+#pragma unroll
+      for (int q = 0; q < JB / 4; ++q) {
+        if (4 * q < jb_used) {                       // warp-uniform
+          const float4 a = a4[q], d = d4[q];
+          acc[4 * q] = fmaf(a.x, dcv, fmaf(d.x, qv, acc[4 * q]));
+          acc[4 * q + 1] = fmaf(a.y, dcv, fmaf(d.y, qv, acc[4 * q + 1]));
+          acc[4 * q + 2] = fmaf(a.z, dcv, fmaf(d.z, qv, acc[4 * q + 2]));
+          acc[4 * q + 3] = fmaf(a.w, dcv, fmaf(d.w, qv, acc[4 * q + 3]));
+        }
+      }
+    }
+  }
+  if (k < H) {
+#pragma unroll
+    for (int i = 0; i < JB; ++i) {
+      const int j = jg * JB + i;
+      if (j < S) {
+        float* o = dctx + ((size_t)j * B + b) * H + k;
+        *o = accumulate ? (*o + acc[i]) : acc[i];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int vmmt_attention_fwd(const float* qp, const float* ctx, const int64_t* lengths,
@@ -187,6 +413,12 @@ extern "C" int vmmt_attention_fwd(const float* qp, const float* ctx, const int64
                                   void* stream) {
   VMMT_REQUIRE(S >= 1 && S <= SMAX, "attention_fwd: src_len %d outside [1,%d]", S, SMAX);
   VMMT_REQUIRE(T >= 1 && B >= 1 && H >= 1, "attention_fwd: bad dims");
+  if (T > 1 && !getenv("VMMT_ATTN_WARP")) {          // sequence mode: tiled kernel (one CTA per 16 queries of one row)
+    const int ntile = ceil_div(T, TT);
+    attn_fwd_tiled_kernel<<<B * ntile, TILE_THREADS, 0, (cudaStream_t)stream>>>(qp, ctx, lengths, align, cvec, T, B,
+                                                                               S, H, ntile);
+    return vmmt_check_launch("attn_fwd_tiled_kernel");
+  }
   int tsplit = ceil_div(T, ATT_WARPS);
   const int want = ceil_div(2 * vmmt_num_sms(), B);
   if (tsplit > want) tsplit = want;
@@ -201,6 +433,17 @@ extern "C" int vmmt_attention_bwd(const float* dcvec, const float* qp, const flo
                                   float* dqp, float* dctx, int accumulate_dctx, int T, int B, int S,
                                   int H, void* stream) {
   VMMT_REQUIRE(S >= 1 && S <= SMAX, "attention_bwd: src_len %d outside [1,%d]", S, SMAX);
+  if (!getenv("VMMT_ATTN_WARP")) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ntile = ceil_div(T, TT), nk = ceil_div(H, 64);
+    attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, 0, st>>>(dcvec, ctx, align, lengths, dscore_ws, dqp, T, B,
+                                                                    S, H, ntile);
+    int rc1 = vmmt_check_launch("attn_bwd_query_tiled_kernel");
+    if (rc1) return rc1;
+    attn_bwd_ctx_tiled_kernel<<<B * nk, TILE_THREADS, 0, st>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H,
+                                                               accumulate_dctx, nk);
+    return vmmt_check_launch("attn_bwd_ctx_tiled_kernel");
+  }
   int tsplit = ceil_div(T, ATT_WARPS);
   const int want = ceil_div(2 * vmmt_num_sms(), B);
   if (tsplit > want) tsplit = want;

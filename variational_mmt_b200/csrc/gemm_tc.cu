@@ -560,8 +560,13 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
       free(h);
     }
   } dump{tracing, trace_buf, grid, s, BN};
-  rc = (BN == 128) ? launch_major<128, 5>(a_mn, b_mn, ta, tb, tc, g, grid, s)
-                   : launch_major<64, 3>(a_mn, b_mn, ta, tb, tc, g, grid, s);
+  static const int deep = getenv("VMMT_GEMM_DEEP") ? atoi(getenv("VMMT_GEMM_DEEP")) : 0;
+  if (deep)
+    rc = (BN == 128) ? launch_major<128, 6>(a_mn, b_mn, ta, tb, tc, g, grid, s)
+                     : launch_major<64, 8>(a_mn, b_mn, ta, tb, tc, g, grid, s);
+  else
+    rc = (BN == 128) ? launch_major<128, 5>(a_mn, b_mn, ta, tb, tc, g, grid, s)
+                     : launch_major<64, 3>(a_mn, b_mn, ta, tb, tc, g, grid, s);
   if (rc) return rc;
   if (finish_act) {
     const int64_t tot = (int64_t)M * N;

@@ -74,6 +74,65 @@ def _anchor(device):
     return torch.empty(0, device=device, requires_grad=True) if torch.is_grad_enabled() else None
 
 
+# ---- side stream: weight / bias gradient GEMMs run off the critical path of the backward pass -------------------
+# The backward's critical path is the chain of recurrences (latency bound, ~110 of the 148 SMs lightly used) plus the
+# input-gradient GEMMs that feed the next layer down.  The weight-gradient GEMMs and bias column sums of every
+# Linear / LSTM layer only feed the optimiser, so they are issued on ONE side stream (hence serialised among
+# themselves: two of them may accumulate into slices of the same parameter) that forks from the main stream after
+# the tensors they read are complete, and is joined before the gradients are consumed (end of the backward pass /
+# Optim.step).  Under CUDA-graph capture the fork / join become graph edges.
+_side = {"stream": None, "keep": [], "dirty": False, "enabled": True}
+
+
+def set_side_stream_enabled(flag):
+    _side["enabled"] = bool(flag)
+
+
+class _OnSide(object):
+    """Issue the enclosed launches on the side stream, ordered after everything already on the current stream."""
+
+    def __enter__(self):
+        self.active = _side["enabled"]
+        if not self.active:
+            return self
+        cur = torch.cuda.current_stream()
+        if _side["stream"] is None or _side["stream"].device != cur.device:
+            _side["stream"] = torch.cuda.Stream(device=cur.device)
+        _side["stream"].wait_stream(cur)
+        if not _side["dirty"]:
+            # first side-stream block of this backward pass: join automatically when the pass ends, so that
+            # whoever reads .grad afterwards (on the stream that called backward) sees complete gradients
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(join_side)
+            except RuntimeError:
+                pass                                   # not inside a backward pass: the caller joins explicitly
+        self.ctx = torch.cuda.stream(_side["stream"])
+        self.ctx.__enter__()
+        _side["dirty"] = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def on_side(*keep):
+    """Context manager; ``keep`` are the tensors the side-stream launches read: they are held until join_side() so
+    that the caching allocator cannot hand their memory to later main-stream work."""
+    if _side["enabled"]:
+        _side["keep"].extend(t for t in keep if t is not None)
+    return _OnSide()
+
+
+def join_side():
+    """The current stream waits for all side-stream work issued so far (call before the gradients are read)."""
+    if _side["dirty"] and _side["stream"] is not None:
+        torch.cuda.current_stream().wait_stream(_side["stream"])
+    _side["dirty"] = False
+    _side["keep"].clear()
+
+
 def grad_buf(p):
     """The tensor parameter gradients are accumulated into (allocated zero-filled on first use)."""
     if p.grad is None:
@@ -157,16 +216,17 @@ class LinearFn(Function):
             L.call("vmmt_act_bwd", fptr(dy), fptr(y), fptr(dpre), dy.numel(), act, stream())
         else:
             dpre = dy
-        if weight.requires_grad:
-            gw = grad_buf(weight)[:, c0:c1]
-            gemm(dpre, x2, gw, N, K, M, a_kmajor=False, b_kmajor=False, accumulate=1)   # dW += dpre^T x
-        if bias is not None and bias.requires_grad:
-            colsum_acc(dpre, M, N, grad_buf(bias))
         dx = None
         if ctx.needs_input_grad[1]:
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
             gemm(dpre, weight[:, c0:c1], dx, M, K, N, b_kmajor=False)                    # dx = dpre W
             dx = dx.view(ctx.xshape)
+        with on_side(dpre, x2):                                                          # off the critical path
+            if weight.requires_grad:
+                gw = grad_buf(weight)[:, c0:c1]
+                gemm(dpre, x2, gw, N, K, M, a_kmajor=False, b_kmajor=False, accumulate=1)   # dW += dpre^T x
+            if bias is not None and bias.requires_grad:
+                colsum_acc(dpre, M, N, grad_buf(bias))
         dadd = dpre.view(*ctx.xshape[:-1], N) if ctx.has_addend and ctx.needs_input_grad[6] else None
         return None, dx, None, None, None, None, dadd
 
@@ -262,35 +322,41 @@ class LSTMLayerFn(Function):
         x2 = x.view(T * N, In)
         dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         drow = None
+        # critical path (main stream): what the layers below / the callers wait for
         for d in range(ndir):
-            w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
-            dg2 = dg[d].view(T * N, 4 * Hd)
-            if dx is not None:                                         # dx (+)= dG W_ih
-                gemm(dg2, w_ih[:, c0c:c1c], dx, T * N, In, 4 * Hd, b_kmajor=False, accumulate=int(d > 0))
-            if w_ih.requires_grad:                                     # dW_ih += dG^T x
-                gemm(dg2, x2, grad_buf(w_ih)[:, c0c:c1c], 4 * Hd, In, T * N, a_kmajor=False,
-                     b_kmajor=False, accumulate=1)
-            if w_hh.requires_grad and T > 1:                           # dW_hh += dG[t]^T h[t -/+ 1]
-                o_d = out[:, :, d * Hd:(d + 1) * Hd]
-                if d == 0:
-                    a_, b_ = dg[d][1:], o_d[:-1]
-                else:
-                    a_, b_ = dg[d][:-1], o_d[1:]
-                # rows (t,n) of the shifted views are contiguous blocks with row strides 4Hd / ndir*Hd
-                gemm(a_.reshape(-1, 4 * Hd), b_.reshape((T - 1) * N, Hd) if ndir == 1 else _rows(b_),
-                     grad_buf(w_hh), 4 * Hd, Hd, (T - 1) * N, a_kmajor=False, b_kmajor=False, accumulate=1)
-            if w_hh.requires_grad and h0 is not None:                  # first step uses h0
-                t0 = 0 if d == 0 else T - 1
-                gemm(dg[d][t0], h0[d], grad_buf(w_hh), 4 * Hd, Hd, N, a_kmajor=False, b_kmajor=False,
-                     accumulate=1)
-            if b_ih.requires_grad and b_hh.requires_grad:              # identical sums: one pass, two outputs
-                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih), grad_buf(b_hh))
-            elif b_ih.requires_grad or b_hh.requires_grad:
-                colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih if b_ih.requires_grad else b_hh))
+            w_ih = weights[4 * d]
+            if dx is not None:                                             # dx (+)= dG W_ih
+                gemm(dg[d].view(T * N, 4 * Hd), w_ih[:, c0c:c1c], dx, T * N, In, 4 * Hd, b_kmajor=False,
+                     accumulate=int(d > 0))
         if rowbias is not None and ctx.needs_input_grad[4]:
             drow = torch.zeros(N, 4 * Hd, device=dev, dtype=torch.float32)
-            for d in range(ndir):                                      # the term enters every direction
+            for d in range(ndir):                                          # the term enters every direction
                 colsum_acc(dg[d].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
+        # weight / bias gradients (side stream): they only feed the optimiser
+        with on_side(dg, x, out, h0):
+            for d in range(ndir):
+                w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
+                dg2 = dg[d].view(T * N, 4 * Hd)
+                if w_ih.requires_grad:                                     # dW_ih += dG^T x
+                    gemm(dg2, x2, grad_buf(w_ih)[:, c0c:c1c], 4 * Hd, In, T * N, a_kmajor=False,
+                         b_kmajor=False, accumulate=1)
+                if w_hh.requires_grad and T > 1:                           # dW_hh += dG[t]^T h[t -/+ 1]
+                    o_d = out[:, :, d * Hd:(d + 1) * Hd]
+                    if d == 0:
+                        a_, b_ = dg[d][1:], o_d[:-1]
+                    else:
+                        a_, b_ = dg[d][:-1], o_d[1:]
+                    # rows (t,n) of the shifted views are contiguous blocks with row strides 4Hd / ndir*Hd
+                    gemm(a_.reshape(-1, 4 * Hd), b_.reshape((T - 1) * N, Hd) if ndir == 1 else _rows(b_),
+                         grad_buf(w_hh), 4 * Hd, Hd, (T - 1) * N, a_kmajor=False, b_kmajor=False, accumulate=1)
+                if w_hh.requires_grad and h0 is not None:                  # first step uses h0
+                    t0 = 0 if d == 0 else T - 1
+                    gemm(dg[d][t0], h0[d], grad_buf(w_hh), 4 * Hd, Hd, N, a_kmajor=False, b_kmajor=False,
+                         accumulate=1)
+                if b_ih.requires_grad and b_hh.requires_grad:              # identical sums: one pass, two outputs
+                    colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih), grad_buf(b_hh))
+                elif b_ih.requires_grad or b_hh.requires_grad:
+                    colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih if b_ih.requires_grad else b_hh))
         if dx is not None:
             dx = dx.view(T, N, In)
         return None, dx, dh0, dc0, drow, None, None, None
