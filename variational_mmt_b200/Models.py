@@ -150,7 +150,10 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         enc_hidden, context = self.encoder(src, lengths)
         if self.conditional:
             assert isinstance(self.inf_net_global, GlobalFullInferenceNetwork)
-            pz0, _ = self.gen_net_global(context, lengths)                       # p(z|x)
+            with ops.branch():                                                   # p(z|x): only the KL needs it in training
+                pz0, _ = self.gen_net_global(context, lengths)
+            if not self.training:
+                ops.join_branch(pz0.mean())
             # target encoder over the transposed ids: recurrence along the batch axis (hazard H1)
             _, tgt_context = self.encoder_tgt(orig_tgt.transpose(0, 1), lengths=None)
             tgt_context = tgt_context.transpose(0, 1)
@@ -162,10 +165,12 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             z0_sample = z0.sample() if self.training else z0.mean().detach()
             pz0 = Normal(torch.zeros_like(z0.params()[0]), torch.ones_like(z0.params()[0]))
             pz0.is_standard = True
+        with ops.branch():                                                       # p(v|z) beside the decoder
+            p_v, _ = self.inf_net_image(z0_sample, context, lengths)
         enc_state = self.decoder.init_decoder_state(src, context, enc_hidden)
         out, dec_state, attns = self.decoder(tgt, context, enc_state if dec_state is None else dec_state,
                                              lengths, image_features=None, z_sample=z0_sample)
-        p_v, _ = self.inf_net_image(z0_sample, context, lengths)
+        ops.join_branch(p_v.mean(), *([] if getattr(pz0, "is_standard", False) else pz0.params()))
         attns["p_global_image_features"] = [p_v]
         attns["ground_truth_global_image_features"] = [img_feats]
         attns["p_latent"] = [pz0]

@@ -133,6 +133,48 @@ def join_side():
     _side["keep"].clear()
 
 
+# ---- branch stream: independent sub-graphs of the forward pass (and, through autograd's per-node streams, of the
+# backward pass) run beside the main chain: prior network and image-feature head beside the decoder ----------------
+_branch = {"stream": None, "enabled": True}
+
+
+class branch(object):
+    """``with ops.branch(): ...`` issues the enclosed module calls on the branch stream, ordered after everything
+    already on the current stream.  Autograd nodes created inside remember that stream, so their backward runs
+    there too.  ``ops.join_branch(*tensors)`` makes the current stream wait and hands the tensors over."""
+
+    def __enter__(self):
+        self.active = _branch["enabled"] and torch.cuda.is_available()
+        if not self.active:
+            return self
+        cur = torch.cuda.current_stream()
+        if _branch["stream"] is None or _branch["stream"].device != cur.device:
+            _branch["stream"] = torch.cuda.Stream(device=cur.device)
+        _branch["stream"].wait_stream(cur)
+        self.ctx = torch.cuda.stream(_branch["stream"])
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_branch(*tensors):
+    if _branch["stream"] is None or not _branch["enabled"]:
+        return
+    cur = torch.cuda.current_stream()
+    cur.wait_stream(_branch["stream"])
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            t.record_stream(cur)
+
+
+def set_branch_enabled(flag):
+    _branch["enabled"] = bool(flag)
+
+
 def grad_buf(p):
     """The tensor parameter gradients are accumulated into (allocated zero-filled on first use)."""
     if p.grad is None:
