@@ -84,6 +84,9 @@ typedef struct VmmtLstmDirBwd {
 } VmmtLstmDirBwd;
 
 size_t vmmt_lstm_workspace_bytes(int ndir, int N, int H);
+/* Cap on the thread-block clusters the next recurrence launches may occupy (0 = as many as are co-resident).  Two
+ * independent recurrences issued on two streams (source encoder / target encoder) share the GPU with it. */
+void vmmt_lstm_set_cluster_budget(int max_clusters);
 int vmmt_lstm_seq_supported(int ndir, int N, int H);
 int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
                       void* workspace, size_t workspace_bytes, void* stream);

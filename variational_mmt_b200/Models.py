@@ -2,6 +2,8 @@
 576-638, 737-1011, 1014-1174).  Same class names, signatures, attributes and state_dict keys; the
 arithmetic runs in libvmmt kernels through ``modules`` / ``ops``.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -138,6 +140,9 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         self.encoder_tgt = kwargs["encoder_tgt"] if self.conditional else None
         if self.encoder_tgt is not None:
             self.encoder_tgt.no_pack_padded_seq = True
+            # concurrent source / target encoders (training): 3 + 4 of the ~7 GPC-sized cluster slots of a B200
+            self.encoder.rnn.cluster_budget = int(os.environ.get("VMMT_ENC_BUDGET", "3")) or None
+            self.encoder_tgt.rnn.cluster_budget = int(os.environ.get("VMMT_TGT_BUDGET", "8")) or None
         self.inf_net_global = kwargs["inf_net_global"]
         self.gen_net_global = kwargs["gen_net_global"]
         self.inf_net_image = kwargs["inf_net_image"]
@@ -147,16 +152,20 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
                 padding_token=None):
         orig_tgt = tgt
         tgt = tgt[:-1]
+        if self.conditional:
+            # target encoder over the transposed ids: recurrence along the batch axis (hazard H1).  It does not depend
+            # on the source encoder: the two stacks run side by side on two streams, each on its share of the SMs
+            with ops.branch():
+                _, tgt_context = self.encoder_tgt(orig_tgt.transpose(0, 1), lengths=None)
+                tgt_context = tgt_context.transpose(0, 1)
         enc_hidden, context = self.encoder(src, lengths)
         if self.conditional:
             assert isinstance(self.inf_net_global, GlobalFullInferenceNetwork)
+            ops.join_branch(tgt_context)
             with ops.branch():                                                   # p(z|x): only the KL needs it in training
                 pz0, _ = self.gen_net_global(context, lengths)
             if not self.training:
                 ops.join_branch(pz0.mean())
-            # target encoder over the transposed ids: recurrence along the batch axis (hazard H1)
-            _, tgt_context = self.encoder_tgt(orig_tgt.transpose(0, 1), lengths=None)
-            tgt_context = tgt_context.transpose(0, 1)
             z0, h = self.inf_net_global(context.detach(), lengths, tgt_context, tgt_lengths, img_feats)
             z0_sample = z0.sample() if self.training else pz0.mean().detach()
         else:

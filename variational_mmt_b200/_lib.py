@@ -47,6 +47,7 @@ SIGNATURES = {
     "vmmt_embedding_bwd": (I, [P, L, P, I, L, P, P]),
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_lstm_seq_supported": (I, [I, I, I]),
+    "vmmt_lstm_set_cluster_budget": (None, [I]),
     "vmmt_lstm_seq_fwd": (I, [C.POINTER(LstmDir), I, P, I, I, I, P, SZ, P]),
     "vmmt_lstm_seq_bwd": (I, [C.POINTER(LstmDirBwd), I, P, I, I, I, P, SZ, P]),
     "vmmt_lstm_cell_fwd": (I, [P, P, P, P, P, P, P, I, I, P]),

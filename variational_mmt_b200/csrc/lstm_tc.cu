@@ -719,6 +719,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
 }
 
 struct TcPlan { int C, G, Ng, Kp, nrg; };
+int g_cluster_budget = 0;     // 0 = all co-resident clusters; > 0: cap (two recurrences sharing the GPU on two streams)
 
 size_t fwd_smem(int Kp, int nrg) {
   return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64;
@@ -776,6 +777,7 @@ void tc_plan(int ndir, int N, int H, int max_clusters, TcPlan* p) {
   p->C = ceil_div(H, UC);
   p->Kp = ceil_div(H, 64) * 64;
   const char* e = getenv("VMMT_LSTM_GROUPS");
+  if (g_cluster_budget > 0) max_clusters = min(max_clusters, g_cluster_budget);
   int gmax = e ? atoi(e) : max(1, max_clusters / ndir);
   int G = max(1, min(gmax, N));
   int Ng = ceil_div(N, G);
@@ -849,6 +851,8 @@ int launch_bwd(TcBwdParams& P, const TcPlan& p, int ndir, int maxc, cudaStream_t
 }  // namespace
 
 bool vmmt_lstm_tc_supported(int ndir, int N, int H) { return tc_shape_ok(ndir, N, H); }
+
+extern "C" void vmmt_lstm_set_cluster_budget(int max_clusters) { g_cluster_budget = max_clusters > 0 ? max_clusters : 0; }
 
 int vmmt_lstm_tc_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, cudaStream_t s) {
   if (!tc_shape_ok(ndir, N, H)) return VMMT_EINVAL;

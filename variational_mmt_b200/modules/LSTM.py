@@ -21,6 +21,7 @@ class LSTM(nn.Module):
         super().__init__()
         self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
         self.dropout, self.bidirectional = float(dropout), bidirectional
+        self.cluster_budget = None       # cap on clusters per recurrence launch (set when two stacks run concurrently)
         ndir = 2 if bidirectional else 1
         k = 1.0 / math.sqrt(hidden_size)
         for l in range(num_layers):
@@ -50,7 +51,8 @@ class LSTM(nn.Module):
                 x = ops.dropout(x, self.dropout, self.training)
             h0 = hx[0][l * ndir:(l + 1) * ndir] if hx is not None else None
             c0 = hx[1][l * ndir:(l + 1) * ndir] if hx is not None else None
-            cfg = {"save": save, "in_cols": in_cols if l == 0 else None}
+            cfg = {"save": save, "in_cols": in_cols if l == 0 else None,
+                   "cluster_budget": self.cluster_budget if self.training else None}
             x, hT, cT = ops.lstm_layer(x, h0, c0, in_bias if l == 0 else None, lengths, cfg, self._weights(l))
             hs.append(hT)
             cs.append(cT)

@@ -325,10 +325,13 @@ class LSTMLayerFn(Function):
             D.reverse = 1 if d == 1 else 0
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
+        L.lib.vmmt_lstm_set_cluster_budget(int(cfg.get("cluster_budget") or 0))
         L.call("vmmt_lstm_seq_fwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
+        L.lib.vmmt_lstm_set_cluster_budget(0)
         if save:
             ctx.save_for_backward(x, out, gates, cs, h0, c0, rowbias, lengths)
             ctx.weights, ctx.cfg = weights, (ndir, T, N, In, Hd, c0c, c1c)
+            ctx.cluster_budget = int(cfg.get("cluster_budget") or 0)
         ctx.set_materialize_grads(False)
         return out, hT, cT
 
@@ -360,7 +363,9 @@ class LSTMLayerFn(Function):
             D.reverse = 1 if d == 1 else 0
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
+        L.lib.vmmt_lstm_set_cluster_budget(ctx.cluster_budget)
         L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
+        L.lib.vmmt_lstm_set_cluster_budget(0)
         x2 = x.view(T * N, In)
         dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         drow = None
