@@ -147,8 +147,12 @@ int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b, const
 int vmmt_generator_nll_bwd(const float* x, const float* W, const float* b, const int64_t* target,
                            int64_t pad_idx, const float* lse, const float* gscale /*device scalar or NULL*/,
                            float scale, int M, int H, int V,
-                           float* dx /*or NULL*/, float* dW /*accumulated*/, float* db /*accumulated*/,
+                           float* dx /*or NULL*/, float* dW /*accumulated, or NULL*/, float* db /*accumulated, or NULL*/,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* dW += dlogits^T x, db += colsum(dlogits) from the dlogits vmmt_generator_nll_bwd left in `workspace` (when it was
+ * called with dW = db = NULL): lets the host issue the weight gradient on another stream. */
+int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW, float* db,
+                             void* stream);
 int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H, int V,
                             float* out /*[M,V]*/, float* lse_ws /*[M]*/, void* stream);
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "vmmt_generator_workspace_bytes": (SZ, [I, I]),
     "vmmt_generator_nll_fwd": (I, [P, P, P, P, L, I, I, I, P, P, P, SZ, P]),
     "vmmt_generator_nll_bwd": (I, [P, P, P, P, L, P, P, F, I, I, I, P, P, P, P, SZ, P]),
+    "vmmt_generator_nll_wgrad": (I, [P, P, I, I, I, P, P, P]),
     "vmmt_generator_logprobs": (I, [P, P, P, I, I, I, P, P, P]),
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),

@@ -139,6 +139,16 @@ struct GemmArgs {
   int tma_store;         // 1: epilogue stores / reduces through the tmC tensor map
   int dbg;
   long long* trace;     // debug: per-CTA timeline (8 slots), or null
+  // fused generator epilogues (vmmt_internal.h: VmmtGenEpi): 0 none, 1 per-row log-sum-exp partials instead of C,
+  // 2 C = softmax-NLL gradient of the tile
+  int epi_mode;
+  float4* lse_part;             // mode 1: [gridDim.x][M] {max, sum exp(x - max), best logit, best column}
+  float* tgt_logit;             // mode 1: [M] logit of the target column (written by the tile that holds it)
+  const int64_t* target;        // modes 1, 2: [M]
+  const float* row_lse;         // mode 2: [M]
+  const float* gscale;          // mode 2: device scalar or null
+  float scale;                  // mode 2
+  long long pad;                // mode 2: ignored target id
 };
 
 template <int ACT>
@@ -200,12 +210,59 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t tmem_b
 // Epilogue through TMA: each warp finishes 32 rows x 32 columns in registers (bias, activation), writes them to
 // a 128B-swizzled 4 KB staging tile (conflict-free 16-byte stores) and one lane issues a bulk tensor store -- or
 // a bulk tensor reduce-add for C += (wgrad accumulation, split-K partial sums).  The TMA clips ragged edges.
-template <int BN, int ACT>
+// Generator forward: the tile's logits never leave the SM.  Each epilogue thread owns one row of the tile (TMEM lane)
+// and folds its BN columns into {running max, sum of exponentials, best logit / column, target logit}.
+template <int BN>
+__device__ __forceinline__ void epilogue_lse(const GemmArgs& g, uint32_t tmem_base, const float* bias_s, int q, int lane,
+                                             int m0, int n0) {
+  const int row = m0 + 32 * q + lane;
+  const long long tg = (row < g.M) ? (long long)g.target[row] : -1;
+  float mx = -INFINITY, sum = 0.f, bestv = -INFINITY, tlogit = 0.f;
+  int besti = 0x7fffffff;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= g.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
+    float x[32], cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      x[j] = (col0 + j < g.N) ? __uint_as_float(v[j]) + bias_s[c * 32 + j] : -INFINITY;
+      if (x[j] > bestv) { bestv = x[j]; besti = col0 + j; }       // ascending columns: ties keep the lowest index
+      cm = fmaxf(cm, x[j]);
+      if ((long long)(col0 + j) == tg) tlogit = x[j];
+    }
+    const float nm = fmaxf(mx, cm);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += __expf(x[j] - nm);          // exp(-inf) = 0 for the columns beyond N
+    sum = sum * __expf(mx - nm) + s;
+    mx = nm;
+  }
+  if (row < g.M) {
+    g.lse_part[(size_t)blockIdx.x * g.M + row] = make_float4(mx, sum, bestv, __int_as_float(besti));
+    if (tg >= n0 && tg < n0 + BN) g.tgt_logit[row] = tlogit;
+  }
+}
+
+template <int BN, int ACT, bool DL = false>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUtensorMap* tmC, uint32_t tmem_base,
                                                   uint32_t stage_u32, const float* bias_s, int q, int lane, int m0,
                                                   int n0, int mode) {
   const int row0 = m0 + 32 * q;
   if (row0 >= g.M) return;
+  // DL: the stored value is the softmax-NLL gradient (exp(x - lse[row]) - [col == target]) * scale, 0 for ignored rows
+  float dl_lse = 0.f, dl_scale = 0.f;
+  long long dl_tg = -1;
+  if (DL) {
+    const int row = row0 + lane;
+    if (row < g.M) {
+      dl_tg = (long long)g.target[row];
+      dl_lse = g.row_lse[row];
+      dl_scale = (dl_tg != g.pad) ? g.scale * (g.gscale ? g.gscale[0] : 1.0f) : 0.f;
+    }
+  }
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     const int col0 = n0 + c * 32;
@@ -225,7 +282,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUten
       for (int e = 0; e < 4; ++e) {
         float t = __uint_as_float(v[4 * j4 + e]);
         if (mode != 3) t += bias_s[c * 32 + 4 * j4 + e];
-        x[e] = act_t<ACT>(t);
+        if (DL) x[e] = (__expf(t - dl_lse) - ((long long)(col0 + 4 * j4 + e) == dl_tg ? 1.0f : 0.0f)) * dl_scale;
+        else x[e] = act_t<ACT>(t);
       }
       const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((j4 ^ (lane & 7)) << 4);
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
@@ -354,12 +412,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 64) trace_mark(g.trace, 4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int mode = (gridDim.z > 1) ? 3 : g.accumulate;        // 0 store, 1 C += v, 2 act(C + v), 3 atomic
-    if (g.tma_store && mode != 2) {
+    if ((g.tma_store && mode != 2) || g.epi_mode == 1) {
       float* bias_s = epi + EPI_WARPS * 2 * 1024;                // [BN] staged once per tile by the 4 warps
       for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS)
         bias_s[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t st = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
+      if (g.epi_mode == 1) {
+        epilogue_lse<BN>(g, tmem_base, bias_s, q, lane, m0, n0);
+      } else if (g.epi_mode == 2) {
+        epilogue_tile_tma<BN, VMMT_ACT_NONE, true>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode);
+      } else
       switch (g.act) {
         case VMMT_ACT_RELU: epilogue_tile_tma<BN, VMMT_ACT_RELU>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
         case VMMT_ACT_TANH: epilogue_tile_tma<BN, VMMT_ACT_TANH>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
@@ -485,6 +548,12 @@ bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const floa
 
 int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
                  int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate, cudaStream_t s) {
+  return vmmt_gemm_tc_ex(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, nullptr, s);
+}
+
+int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
+                    int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
+                    const VmmtGenEpi* epi, cudaStream_t s) {
   const bool a_mn = !a_kmajor, b_mn = !b_kmajor;
   const int nsm = vmmt_num_sms();
   const int tiles_m = ceil_div(M, BM);
@@ -492,10 +561,10 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
   // (tile width, split-K) from a small cost model in SM cycles: a CTA costs a fixed prologue + epilogue plus
   // its k-blocks; 128-wide tiles run one CTA per SM (shared-memory-bandwidth bound, ~450 cycles per k-block),
   // 64-wide tiles two per SM; split-K needs a linear epilogue (an activation is applied by a finishing pass)
-  const bool can_split = (accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE);
+  const bool can_split = epi == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
   int BN = 128, splits = 1;
   double best = 1e30;
-  for (int bn = 64; bn <= 128; bn *= 2) {
+  for (int bn = (epi ? 128 : 64); bn <= 128; bn *= 2) {
     const int tiles = tiles_m * ceil_div(N, bn);
     const int slots = nsm * (bn == 64 ? 2 : 1);
     const int max_split = can_split ? min(32, max(1, nkb / 4)) : 1;
@@ -527,7 +596,10 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
   if (rc) return rc;
   static int dbg = getenv("VMMT_GEMM_DBG") ? atoi(getenv("VMMT_GEMM_DBG")) : 0;
   // C through TMA (store / reduce-add) when its base and pitch are 16-byte aligned; else direct stores
-  const int tma_store = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && accumulate != 2 && !getenv("VMMT_GEMM_NO_TMA_STORE")) ? 1 : 0;
+  const bool lse_mode = epi != nullptr && epi->mode == 1;        // no C at all
+  const int tma_store = (!lse_mode && ((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && accumulate != 2 &&
+                         (epi != nullptr || !getenv("VMMT_GEMM_NO_TMA_STORE"))) ? 1 : 0;
+  if (epi != nullptr && epi->mode == 2 && !tma_store) return VMMT_EINVAL;   // the gradient epilogue lives in the TMA-store path
   CUtensorMap tc;
   if (tma_store) {
     rc = make_map(&tc, C, N, M, ldc, 32, false, true);
@@ -535,7 +607,18 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
   } else {
     tc = ta;
   }
-  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, nullptr};
+  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, nullptr,
+             0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0};
+  if (epi) {
+    g.epi_mode = epi->mode;
+    g.lse_part = reinterpret_cast<float4*>(epi->lse_part);
+    g.tgt_logit = epi->tgt_logit;
+    g.target = epi->target;
+    g.row_lse = epi->row_lse;
+    g.gscale = epi->gscale;
+    g.scale = epi->scale;
+    g.pad = epi->pad;
+  }
   dim3 grid(ceil_div(N, BN), tiles_m, splits);
   static long long* trace_buf = nullptr;
   const bool tracing = getenv("VMMT_GEMM_TRACE") != nullptr;

@@ -58,6 +58,34 @@ row_lse_kernel(const float* __restrict__ logits, const int64_t* __restrict__ tar
   }
 }
 
+// fused path: combine the per-tile partials {max, sumexp, best, besti} of a row -> lse, row statistics
+__global__ void lse_combine_kernel(const float4* __restrict__ part, const float* __restrict__ tgt_logit,
+                                   const int64_t* __restrict__ target, int64_t pad, int M, int ntile,
+                                   float* __restrict__ lse, float* __restrict__ rowstat) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float mx = -INFINITY, bestv = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int t = 0; t < ntile; ++t) {
+    const float4 p = part[(size_t)t * M + row];
+    mx = fmaxf(mx, p.x);
+    const int bi = __float_as_int(p.w);
+    if (p.z > bestv || (p.z == bestv && bi < besti)) { bestv = p.z; besti = bi; }
+  }
+  float s = 0.f;
+  for (int t = 0; t < ntile; ++t) {
+    const float4 p = part[(size_t)t * M + row];
+    s += p.y * expf(p.x - mx);
+  }
+  const float Lr = mx + logf(s);
+  lse[row] = Lr;
+  const int64_t tg = target[row];
+  const bool on = tg != pad;
+  rowstat[row * 3 + 0] = on ? (Lr - tgt_logit[row]) : 0.f;
+  rowstat[row * 3 + 1] = on ? 1.f : 0.f;
+  rowstat[row * 3 + 2] = (on && besti == (int)tg) ? 1.f : 0.f;
+}
+
 // deterministic single-block reduction of the per-row statistics
 __global__ void reduce_rowstat_kernel(const float* __restrict__ rowstat, int M, float* __restrict__ out) {
   __shared__ float red[32];
@@ -94,6 +122,9 @@ __global__ void logprob_kernel(float* __restrict__ logits, const float* __restri
 extern "C" int vmmt_gemm(const float*, int64_t, int, const float*, int64_t, int, float*, int64_t,
                          int, int, int, const float*, int, int, void*);
 
+extern "C" int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW,
+                                        float* db, void* stream);
+
 extern "C" size_t vmmt_generator_workspace_bytes(int M, int V) {
   return ((size_t)M * V + (size_t)M * 4) * sizeof(float);
 }
@@ -108,7 +139,25 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
   }
   float* logits = (float*)workspace;
   float* rowstat = logits + (size_t)M * V;
-  int rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+  int rc;
+  // tensor-core mode: log-sum-exp / target logit / argmax are folded into the GEMM epilogue; the logits of a tile
+  // live in tensor memory and registers only.  Partials: [ceil(V/128)][M] float4 at the head of the workspace.
+  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_GEN_UNFUSED") &&
+      vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) {
+    const int ntile = ceil_div(V, 128);
+    float* part = logits;                                  // ntile * M * 4 floats  <<  M * V
+    float* tgt_logit = part + (size_t)ntile * M * 4;
+    VmmtGenEpi epi{1, part, tgt_logit, target, nullptr, nullptr, 1.0f, (long long)pad_idx};
+    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, (cudaStream_t)stream);
+    if (rc) return rc;
+    lse_combine_kernel<<<ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(part), tgt_logit, target, pad_idx, M, ntile, lse, rowstat);
+    rc = vmmt_check_launch("lse_combine");
+    if (rc) return rc;
+    reduce_rowstat_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowstat, M, stats3);
+    return vmmt_check_launch("reduce_rowstat");
+  }
+  rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
   if (rc) return rc;
   row_lse_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, target, pad_idx, lse, rowstat, V);
   rc = vmmt_check_launch("row_lse");
@@ -128,19 +177,39 @@ extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const floa
   }
   float* dl = (float*)workspace;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = vmmt_gemm(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
-  if (rc) return rc;
-  dlogits_kernel<<<dim3(ceil_div(V, 256), M), 256, 0, s>>>(dl, lse, target, pad_idx, gscale, scale, V);
-  rc = vmmt_check_launch("dlogits");
-  if (rc) return rc;
+  int rc = VMMT_EINVAL;
+  // tensor-core mode: the recomputed logits are turned into dlogits in the GEMM epilogue (one pass over M x V)
+  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_GEN_UNFUSED") && (V & 3) == 0 &&
+      vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, dl, V, M, V, H)) {
+    VmmtGenEpi epi{2, nullptr, nullptr, target, lse, gscale, scale, (long long)pad_idx};
+    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, s);
+  }
+  if (rc != VMMT_OK) {
+    rc = vmmt_gemm(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+    if (rc) return rc;
+    dlogits_kernel<<<dim3(ceil_div(V, 256), M), 256, 0, s>>>(dl, lse, target, pad_idx, gscale, scale, V);
+    rc = vmmt_check_launch("dlogits");
+    if (rc) return rc;
+  }
   if (dx) {   // dX[M,H] = dl[M,V] W[V,H]
     rc = vmmt_gemm(dl, V, 1, W, H, 0, dx, H, M, H, V, nullptr, VMMT_ACT_NONE, 0, stream);
     if (rc) return rc;
   }
-  // dW[V,H] += dl^T[V,M] x[M,H]
-  rc = vmmt_gemm(dl, V, 0, x, H, 0, dW, H, V, H, M, nullptr, VMMT_ACT_NONE, 1, stream);
-  if (rc) return rc;
-  return vmmt_colsum_acc(dl, V, M, V, db, nullptr, stream);
+  if (dW == nullptr && db == nullptr) return VMMT_OK;      // weight gradients taken later by vmmt_generator_nll_wgrad
+  return vmmt_generator_nll_wgrad(x, workspace, M, H, V, dW, db, stream);
+}
+
+// dW[V,H] += dl^T[V,M] x[M,H];  db += colsum(dl), with dl = the dlogits vmmt_generator_nll_bwd left in `workspace`
+// (lets the caller put the weight gradient on another stream, off the critical path of the backward pass)
+extern "C" int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW,
+                                        float* db, void* stream) {
+  const float* dl = (const float*)workspace;
+  if (dW) {
+    int rc = vmmt_gemm(dl, V, 0, x, H, 0, dW, H, V, H, M, nullptr, VMMT_ACT_NONE, 1, stream);
+    if (rc) return rc;
+  }
+  if (db) return vmmt_colsum_acc(dl, V, M, V, db, nullptr, stream);
+  return VMMT_OK;
 }
 
 extern "C" int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H,

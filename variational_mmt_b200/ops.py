@@ -589,8 +589,10 @@ class VILossFn(Function):
         wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
         L.call("vmmt_generator_nll_bwd", fptr(out2d), fptr(ctx.gen_w), fptr(ctx.gen_b), ptr(target),
-               cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), fptr(grad_buf(ctx.gen_w)),
-               fptr(grad_buf(ctx.gen_b)), fptr(ws), wsb, stream())
+               cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), None, None, fptr(ws), wsb, stream())
+        with on_side(ws, out2d):                               # generator weight gradient: off the critical path
+            L.call("vmmt_generator_nll_wgrad", fptr(out2d), fptr(ws), M, H, V, fptr(grad_buf(ctx.gen_w)),
+                   fptr(grad_buf(ctx.gen_b)), stream())
         B, Z = mu_q.shape
         dmq, dsq = torch.empty_like(mu_q), torch.empty_like(sd_q)
         dmp = torch.empty_like(mu_q) if mu_p is not None else None
