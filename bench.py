@@ -344,7 +344,8 @@ def run_ours(args):
                        "gemm": "tf32 tcgen05 (fp32 storage, fp32 accumulate)" if _lib.lib.vmmt_get_gemm_mode() == 0
                                else "fp32 simt",
                        "parallelism": "dp%d" % n_gpus,
-                       "launch": "eager" if graphed is None else "cuda graph (fwd+loss+bwd) + eager all-reduce/clip/Adam",
+                       "exchange": optim.exchange_in_use,
+                       "launch": "eager" if graphed is None else "cuda graph (fwd+loss+bwd) + eager gradient exchange/clip/Adam",
                        "l2": "no flush: each step streams params+grads+Adam moments (%.0f MB) > 126 MB L2 and "
                              "rotates over %d different batches" % (16.0 * n_params / 1e6, NB)},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,

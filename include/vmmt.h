@@ -163,6 +163,31 @@ int vmmt_adam_clip_step(float* param, const float* grad, float* exp_avg, float* 
                         const float* sqnorm /*device scalar*/, float max_norm, float grad_scale, float lr,
                         float beta1, float beta2, float eps, int64_t step, void* stream);
 
+/* ---- data-parallel optimiser step over NVLink peer memory (csrc/peer.cu).  The reference has no multi-GPU path
+ * (train_mm_vi_model1.py:73-75); an N-rank step must equal its `-accum_count N` step (TrainerMultimodal.py:342-346,
+ * 625-718: gradients ADD, then one clip_grad_norm + Adam, Optim.py:69-70,94-96).  Every rank owns one segment
+ *   [signal block (vmmt_peer_signal_bytes) | ... flat params at param_off ... | ... flat grads at grad_off ...]
+ * allocated with vmmt_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; the library owns this memory because it must be
+ * IPC-exportable) and maps the others with vmmt_peer_open.  `segments[j]` = base of rank j's segment as mapped here. */
+size_t vmmt_peer_signal_bytes(void);
+int vmmt_peer_handle_bytes(void);
+int vmmt_peer_alloc(size_t bytes, void** ptr, void* handle_out /* vmmt_peer_handle_bytes() bytes */);
+int vmmt_peer_open(const void* handle, void** ptr);
+int vmmt_peer_close(void* ptr);
+int vmmt_peer_free(void* ptr);
+/* cross-GPU barrier kernel on `stream` (flag words in the signal blocks, device-resident generation counter). */
+int vmmt_peer_barrier(void* const* segments, int rank, int world, void* stream);
+size_t vmmt_peer_adam_workspace_bytes(void);
+/* [*lo, *hi) = the floats of an n-float flat buffer rank `rank` reduces and updates; returns the slice capacity
+ * (floats) every rank allocates for gsum / exp_avg / exp_avg_sq. */
+int64_t vmmt_peer_slice(int64_t n, int world, int rank, int64_t* lo, int64_t* hi);
+/* barrier -> reduce-scatter (P2P loads, rank-ordered sum) + ||g||^2 share -> barrier -> clip + Adam on the slice,
+ * new parameters stored into all N parameter buffers (P2P stores) -> barrier.  sqnorm_out (optional) receives the
+ * squared global norm of the summed gradient.  No NCCL, no host synchronisation, CUDA-graph capturable. */
+int vmmt_peer_adam_step(void* const* segments, size_t param_off, size_t grad_off, int rank, int world, int64_t n,
+                        float* gsum, float* exp_avg, float* exp_avg_sq, float* sqnorm_out, float max_norm, float lr,
+                        float beta1, float beta2, float eps, int64_t step, void* workspace, void* stream);
+
 /* ---- beam search bookkeeping (Beam.py:64-123; Models.py:589-594) */
 /* step index = *step_dev when step_dev != NULL (device-resident: the decode step is replayed from a CUDA graph), else
  * `step`; tok_cur / prev_cur ([K,B], optional) receive the newest tokens / back pointers at fixed addresses. */

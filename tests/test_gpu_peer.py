@@ -1,0 +1,102 @@
+"""-m gpu: the NVLink peer-memory optimiser step (csrc/peer.cu: reduce-scatter -> clip + Adam on the rank's slice ->
+all-gather) against the replicated path (vmmt_sqnorm + vmmt_adam_clip_step, Optim.py:69-70,94-96 semantics).
+
+Single GPU: world = 1 exercises the same kernels with the rank as its own only peer.  Two GPUs (skipped otherwise):
+the peer step must leave both replicas identical and equal to the NCCL all-reduce step on the same gradients.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _toy_module(n_sizes, dev):
+    import variational_mmt_b200  # noqa: F401
+    from variational_mmt_b200.flat import FlatParamsMixin
+
+    class Toy(FlatParamsMixin, torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(7)
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(n, generator=g) * 0.1) for n in n_sizes])
+    m = Toy().to(dev)
+    m.flatten_parameters()
+    return m
+
+
+def test_peer_step_world1_equals_replicated_step(cuda_device):
+    import variational_mmt_b200 as vm
+    sizes = [1000, 37, 4096 * 33 + 5, 3, 250000]        # ragged sizes: every tensor is padded to 4 floats
+    ma, mb = _toy_module(sizes, cuda_device), _toy_module(sizes, cuda_device)
+    oa = vm.Optim("adam", 0.002, 5, exchange="nccl")
+    ob = vm.Optim("adam", 0.002, 5, exchange="peer")
+    oa.set_parameters(ma.parameters())
+    ob.set_parameters(mb.parameters())
+    assert ob.peer is not None and ob.peer.world == 1 and oa.peer is None
+    assert torch.equal(oa.flat, ob.flat)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for it in range(4):
+        scale = 3.0 if it % 2 == 0 else 1e-3              # clipped and unclipped steps
+        grad = torch.randn(oa.gflat.numel(), device=cuda_device, generator=g) * scale
+        ma.zero_grad(); mb.zero_grad()
+        oa.gflat.copy_(grad); ob.gflat.copy_(grad)
+        oa.step(); ob.step()
+        torch.cuda.synchronize()
+        ref_sq = float((grad.double() ** 2).sum())
+        assert abs(float(ob._sq) - ref_sq) <= 1e-5 * ref_sq
+        assert abs(float(oa._sq) - ref_sq) <= 1e-5 * ref_sq
+        # same arithmetic per element; only the clip coefficient may differ in its last bit
+        assert torch.allclose(oa.flat, ob.flat, rtol=2e-6, atol=1e-8), float((oa.flat - ob.flat).abs().max())
+    # parameters are still views of the (peer) flat buffer
+    assert mb.ps[0].data_ptr() == ob.flat.data_ptr()
+    assert mb.ps[0].grad.data_ptr() == ob.gflat.data_ptr()
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import distributed as D
+    D.init_from_env(backend="nccl", device=dev)
+    sizes = [1000, 37, 4096 * 33 + 5, 3, 250000]
+    res = {}
+    for mode in ("nccl", "peer"):
+        m = _toy_module(sizes, dev)
+        o = vm.Optim("adam", 0.002, 5, exchange=mode)
+        o.set_parameters(m.parameters())
+        if mode == "peer":
+            assert o.peer is not None and o.peer.world == world, "peer exchange did not come up"
+        for it in range(5):
+            g = torch.Generator(device="cuda").manual_seed(1000 * it + rank)     # a different gradient per rank
+            grad = torch.randn(o.gflat.numel(), device=dev, generator=g) * (2.0 if it % 2 == 0 else 1e-3)
+            m.zero_grad()
+            o.gflat.copy_(grad)
+            o.step()
+        torch.cuda.synchronize()
+        res[mode] = o.flat.cpu().numpy().copy()
+        res[mode + "_sq"] = float(o._sq) if mode == "peer" else float(o.grad_norm() ** 2)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), nccl=res["nccl"], peer=res["peer"], peer_sq=res["peer_sq"],
+             nccl_sq=res["nccl_sq"])
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_two_gpu_peer_step_equals_nccl_step(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29650 + (os.getpid() % 100)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(2)]
+    assert np.array_equal(r0["peer"], r1["peer"])                        # replicas bit-identical
+    assert np.array_equal(r0["nccl"], r1["nccl"])
+    assert np.allclose(r0["peer"], r0["nccl"], rtol=2e-6, atol=1e-8), float(np.abs(r0["peer"] - r0["nccl"]).max())
+    assert abs(float(r0["peer_sq"]) - float(r0["nccl_sq"])) <= 1e-5 * float(r0["nccl_sq"])

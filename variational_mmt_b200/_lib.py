@@ -75,6 +75,16 @@ SIGNATURES = {
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),
     "vmmt_adam_clip_step": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),
+    "vmmt_peer_signal_bytes": (SZ, []),
+    "vmmt_peer_handle_bytes": (I, []),
+    "vmmt_peer_alloc": (I, [SZ, C.POINTER(P), P]),
+    "vmmt_peer_open": (I, [P, C.POINTER(P)]),
+    "vmmt_peer_close": (I, [P]),
+    "vmmt_peer_free": (I, [P]),
+    "vmmt_peer_barrier": (I, [P, I, I, P]),
+    "vmmt_peer_adam_workspace_bytes": (SZ, []),
+    "vmmt_peer_slice": (L, [L, I, I, C.POINTER(L), C.POINTER(L)]),
+    "vmmt_peer_adam_step": (I, [P, SZ, SZ, I, I, L, P, P, P, P, F, F, F, F, F, L, P, P]),
     "vmmt_beam_advance": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
     "vmmt_beam_record": (I, [P, P, P, L, P]),
     "vmmt_beam_reorder": (I, [P, P, P, P, I, I, I, I, P]),

@@ -241,7 +241,7 @@ __device__ __forceinline__ void epilogue_lse(const GemmArgs& g, uint32_t tmem_ba
     mx = nm;
   }
   if (row < g.M) {
-    g.lse_part[(size_t)blockIdx.x * g.M + row] = make_float4(mx, sum, bestv, __int_as_float(besti));
+    g.lse_part[(size_t)(n0 / BN) * g.M + row] = make_float4(mx, sum, bestv, __int_as_float(besti));
     if (tg >= n0 && tg < n0 + BN) g.tgt_logit[row] = tlogit;
   }
 }
@@ -323,7 +323,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)STAGES * STAGE + epi_bytes() + 16 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // Tile rasterisation: CTAs are scheduled in linear blockIdx order; consecutive CTAs walk DOWN a group of GROUP_M
+  // row-tiles before moving to the next column-tile, so the ~148 co-resident CTAs share GROUP_M A-tiles and ~10 B-tiles
+  // out of L2 instead of one A-tile and 148 B-tiles (the generator's [V,H] weight is larger than L2 at cfg5: without
+  // this every row-tile sweep re-read all of it from HBM -- 39 GB of DRAM traffic for 0.3 GB of operands).
+  int tile_m, tile_n;
+  {
+    constexpr int GROUP_M = 16;
+    const int tiles_n = gridDim.x, tiles_m = gridDim.y;
+    const int lin = blockIdx.x + tiles_n * blockIdx.y;
+    const int grp = lin / (GROUP_M * tiles_n);
+    const int first_m = grp * GROUP_M;
+    const int gm = min(GROUP_M, tiles_m - first_m);
+    const int within = lin - grp * GROUP_M * tiles_n;
+    tile_m = first_m + within % gm;
+    tile_n = within / gm;
+  }
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
   const int nkb_total = (g.K + BK - 1) / BK;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + g.kb_per_split);

@@ -11,8 +11,17 @@ target encoder couples the examples inside a batch (SURVEY.md hazard H1).  Decod
 sentences are independent and are simply dealt out to the ranks.
 
 Works on any torch.distributed backend: "nccl" on the GPUs (NVLink 5 / NVSwitch), "gloo" in the CPU tests.
+
+On one NVSwitch box the gradient exchange does not go through NCCL at all: ``PeerExchange`` places every
+rank's flat parameter and gradient buffers in cudaIpc-exported memory and the optimiser step becomes
+reduce-scatter (P2P loads) -> clip + Adam on the rank's 1/N slice -> all-gather (P2P stores), fused into
+the update kernels themselves (csrc/peer.cu).  torch.distributed then only
+carries the 64-byte IPC handles once and a few scalars.
 """
+import ctypes
 import os
+import socket
+import sys
 
 import torch
 import torch.distributed as dist
@@ -82,3 +91,104 @@ def reduce_statistics(vec):
     if is_active():
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+class _RawDeviceBuffer(object):
+    """__cuda_array_interface__ view of library-allocated device memory (zero copy into torch)."""
+
+    def __init__(self, ptr, n_floats, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerExchange(object):
+    """One cudaIpc segment per rank = [signal block | flat params | flat grads], opened by every peer.
+
+    ``PeerExchange.create(n_floats, device)`` is collective over the default process group (or local when
+    torch.distributed is not up: world = 1, used by the single-GPU kernel tests).  Returns None -- on every
+    rank alike -- when the ranks are not on one host or a peer mapping fails; the caller then keeps the
+    NCCL all-reduce path (still GPU; reported in bench.py's config)."""
+
+    def __init__(self):
+        self.rank, self.world = rank_world()
+        self.segments = None           # ctypes array of `world` base pointers (index = rank)
+        self.base = None
+        self.flat = self.gflat = None
+        self._opened = []
+
+    @classmethod
+    def create(cls, n_floats, device):
+        from . import _lib as L
+        self = cls()
+        sig = int(L.lib.vmmt_peer_signal_bytes())
+        self.n = int(n_floats)
+        self.param_off = sig
+        self.grad_off = sig + ((self.n * 4 + 255) // 256) * 256
+        nbytes = self.grad_off + ((self.n * 4 + 255) // 256) * 256
+        hb = int(L.lib.vmmt_peer_handle_bytes())
+        handle = ctypes.create_string_buffer(hb)
+        base = ctypes.c_void_p()
+        ok, why = True, ""
+        with torch.cuda.device(device):
+            rc = L.lib.vmmt_peer_alloc(nbytes, ctypes.byref(base), handle)
+        if rc != 0:
+            ok, why = False, "alloc: " + L.last_error()
+        self.base = base.value
+        ptrs = [None] * self.world
+        ptrs[self.rank] = self.base
+        if self.world > 1:
+            infos = [None] * self.world
+            dist.all_gather_object(infos, (socket.gethostname(), bytes(handle.raw), ok))
+            if len({h for h, _b, _o in infos}) != 1:
+                ok, why = False, "ranks span several hosts"
+            if ok and all(o for _h, _b, o in infos):
+                with torch.cuda.device(device):
+                    for j, (_h, hbytes, _o) in enumerate(infos):
+                        if j == self.rank:
+                            continue
+                        pp = ctypes.c_void_p()
+                        if L.lib.vmmt_peer_open(hbytes, ctypes.byref(pp)) != 0:
+                            ok, why = False, "open rank %d: %s" % (j, L.last_error())
+                            break
+                        ptrs[j] = pp.value
+                        self._opened.append(pp.value)
+            else:
+                ok = False
+            oks = [None] * self.world
+            dist.all_gather_object(oks, (ok, why))
+            if not all(o for o, _w in oks):
+                if self.rank == 0:
+                    sys.stderr.write("variational_mmt_b200: NVLink peer exchange unavailable (%s); using the NCCL "
+                                     "all-reduce\n" % "; ".join(w for _o, w in oks if w))
+                self.close()
+                return None
+        elif not ok:
+            raise RuntimeError("PeerExchange: " + why)
+        self.segments = (ctypes.c_void_p * self.world)(*ptrs)
+        self.flat = torch.as_tensor(_RawDeviceBuffer(self.base + self.param_off, self.n, self), device=device)
+        self.gflat = torch.as_tensor(_RawDeviceBuffer(self.base + self.grad_off, self.n, self), device=device)
+        self.device = device
+        return self
+
+    def slice_bounds(self):
+        """(lo, hi, capacity) in floats of the slice this rank reduces and updates."""
+        from . import _lib as L
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        cap = L.lib.vmmt_peer_slice(self.n, self.world, self.rank, ctypes.byref(lo), ctypes.byref(hi))
+        return int(lo.value), int(hi.value), int(cap)
+
+    def barrier(self):
+        """Device-side barrier over the peer segments on the current stream (no host synchronisation)."""
+        from . import _lib as L
+        L.call("vmmt_peer_barrier", self.segments, self.rank, self.world, L.stream())
+
+    def close(self):
+        from . import _lib as L
+        for p in self._opened:
+            L.lib.vmmt_peer_close(p)
+        self._opened = []
+        if self.base is not None and self.flat is None:       # never handed out as tensors: safe to free
+            L.lib.vmmt_peer_free(self.base)
+            self.base = None

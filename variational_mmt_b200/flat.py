@@ -5,12 +5,33 @@ The backward kernels accumulate straight into ``param.grad`` views of the flat g
 launches (see Optim.py).  Parameter identity, names and shapes are untouched, so state_dicts saved
 by the reference load unchanged.
 """
+import weakref
+
 import torch
 
+_OWNERS = {}          # data_ptr of a flat parameter buffer -> weakref of the module that owns it
 
-def flatten_parameters(module):
+
+def owner_of(param):
+    """The module whose flat buffer holds ``param`` (None when it is not in one)."""
+    ref = _OWNERS.get(param.data.untyped_storage().data_ptr())
+    return ref() if ref is not None else None
+
+
+def padded_numel(module):
+    """Length (floats) of the flat buffers ``flatten_parameters(module)`` needs."""
+    seen, total = set(), 0
+    for p in module.parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            total += ((p.numel() + 3) // 4) * 4
+    return total
+
+
+def flatten_parameters(module, buffers=None):
     """Re-point every parameter of ``module`` (and its ``.grad``) into flat buffers.
-    Idempotent; call again after moving the module to another device."""
+    Idempotent; call again after moving the module to another device.  ``buffers=(flat, gflat)`` places
+    them in caller-provided fp32 storage (the NVLink peer segment of distributed.PeerExchange)."""
     params = []
     seen = set()
     for p in module.parameters():
@@ -22,8 +43,13 @@ def flatten_parameters(module):
     dev = params[0].device
     sizes = [((p.numel() + 3) // 4) * 4 for p in params]          # keep every tensor 16-byte aligned
     total = sum(sizes)
-    flat = torch.zeros(total, device=dev, dtype=torch.float32)
-    gflat = torch.zeros(total, device=dev, dtype=torch.float32)
+    if buffers is None:
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        gflat = torch.zeros(total, device=dev, dtype=torch.float32)
+    else:
+        flat, gflat = buffers
+        assert flat.numel() == total and gflat.numel() == total and flat.device == dev, "flat buffers: wrong size/device"
+        gflat.zero_()
     off = 0
     with torch.no_grad():
         for p, n in zip(params, sizes):
@@ -33,6 +59,7 @@ def flatten_parameters(module):
             p.grad = gflat[off: off + p.numel()].view(p.shape)
             off += n
     module._flat_params, module._flat_grads = flat, gflat
+    _OWNERS[flat.untyped_storage().data_ptr()] = weakref.ref(module)
     return flat, gflat
 
 
