@@ -555,9 +555,15 @@ def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
     flops = 2.0 * M * H * V
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"] / 2.0        # TF32 runs at half the bf16 tensor rate
-    return {"kernel": "vmmt_generator_nll_fwd (M=%d,H=%d,V=%d)" % (M, H, V), "bound": "tensor",
+    name = "vmmt_generator_nll_fwd (M=%d,H=%d,V=%d)" % (M, H, V)
+    traffic = None                           # DRAM bytes per launch from the committed `ncu --set full` capture, if any
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = (json.load(f).get(name) or {}).get("dram_bytes")
+    return {"kernel": name, "bound": "tensor",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "ms": ms,
+            "traffic": traffic, "algorithmic_bytes": (M * H + V * H + V) * 4.0, "ms": ms,
             "peak_source": "%s bf16 burst %.0f TF/s / 2 (tf32 operands)" % (how, peaks["bf16_tflops"])}
 
 

@@ -79,3 +79,37 @@ def test_batched_decode_equals_sentence_by_sentence(name, graph, cuda_device):
                 _check(ret, i, arr, i, 1e-4)
     finally:
         _lib.lib.vmmt_set_gemm_mode(0)
+
+
+def test_in_process_validation_translate_equals_sentence_by_sentence(cuda_device, tmp_path):
+    """translate_dataset (batched, in place on the live training model) returns, in corpus order, what
+    the per-sentence decode of translate_mm_vi.py returns, and restores train mode."""
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import _lib, io
+    _lib.lib.vmmt_set_gemm_mode(1)
+    try:
+        cfg = synth.TINY
+        params = synth.make_params(cfg, 3435, 0.1)
+        model, fields = build_cuda_model(cfg, params)
+        model.train()
+        ds = io.TripletDataset.synthetic(23, v_src=cfg.v_src, v_tgt=cfg.v_tgt, seed=4, src_max=12, tgt_max=10)
+        out = tmp_path / "hyp.txt"
+        hyps = vm.translate.translate_dataset(model, fields, ds, batch_size=7, beam_size=1, max_length=20, output=str(out))
+        assert model.training
+        model.eval()
+        tr = vm.TranslatorMultimodalVI(model, fields, beam_size=1, n_best=1, max_length=20,
+                                       global_scorer=vm.GNMTGlobalScorer(0., -0.), cuda=True,
+                                       test_img_feats=np.zeros((1, 1), np.float32), multimodal_model_type="vi-model1")
+        itos = fields["tgt"].vocab.itos
+        for i in range(len(ds)):
+            b = _B()
+            b.batch_size = 1
+            s = ds.src_flat[ds.src_off[i]: ds.src_off[i + 1]]
+            b.src = (torch.as_tensor(s).view(-1, 1), torch.as_tensor([len(s)]))
+            words = [itos[t] for t in tr.translate_batch(b, None, i)["predictions"][0][0]]
+            if words and words[-1] == "</s>":
+                words = words[:-1]
+            assert hyps[i] == words, f"sentence {i}"
+        assert out.read_text().splitlines() == [" ".join(h) for h in hyps]
+    finally:
+        _lib.lib.vmmt_set_gemm_mode(0)

@@ -26,3 +26,17 @@ def test_lstm_stepwise_path(gemm_mode, monkeypatch):
     monkeypatch.setenv("VMMT_LSTM_STEPWISE", "1")
     bad = [(l, e, t) for l, e, t in kc.check_lstm() if not (e <= t * gemm_mode)]
     assert not bad, "\n".join(f"{l}: err {e:.3e} > tol {t * gemm_mode:.1e}" for l, e, t in bad)
+
+
+def test_image_feature_table_gather(cuda_device):
+    """Device-resident feature table + row gather by batch.indices == the reference's host fancy index
+    (onmt/TrainerMultimodal.py:632-639)."""
+    import numpy as np
+    import torch
+    from variational_mmt_b200 import io
+    rng = np.random.RandomState(0)
+    feats = np.abs(rng.normal(0, 1, (777, 2048))).astype(np.float32)
+    table = io.ImageFeatureTable(feats, cuda_device)
+    for idx in ([0], [776, 0, 5, 5, 123], rng.randint(0, 777, 40).tolist()):
+        got = table.gather(torch.as_tensor(idx, dtype=torch.int64)).cpu().numpy()
+        assert np.array_equal(got, feats[np.asarray(idx)])            # bit-exact: a copy

@@ -90,13 +90,18 @@ def _worker(rank, world, port, out_dir):
     torch.distributed.destroy_process_group()
 
 
-def test_two_gpu_peer_step_equals_nccl_step(tmp_path):
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    port = 29650 + (os.getpid() % 100)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    r0, r1 = [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(2)]
-    assert np.array_equal(r0["peer"], r1["peer"])                        # replicas bit-identical
-    assert np.array_equal(r0["nccl"], r1["nccl"])
-    assert np.allclose(r0["peer"], r0["nccl"], rtol=2e-6, atol=1e-8), float(np.abs(r0["peer"] - r0["nccl"]).max())
-    assert abs(float(r0["peer_sq"]) - float(r0["nccl_sq"])) <= 1e-5 * float(r0["nccl_sq"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_peer_step_equals_nccl_step(tmp_path, world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = 29650 + (os.getpid() % 100) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rs = [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(world)]
+    for r in rs[1:]:
+        assert np.array_equal(rs[0]["peer"], r["peer"])                    # replicas bit-identical
+        assert np.array_equal(rs[0]["nccl"], r["nccl"])
+    # vs NCCL: the same N-term sums in another order (and for N = 2 the very same sum); a near-cancelling sum may
+    # flip the sign of Adam's first normalised step, hence a fraction instead of allclose
+    bad = ~np.isclose(rs[0]["peer"], rs[0]["nccl"], rtol=2e-6, atol=1e-8)
+    assert bad.mean() < 1e-5, (int(bad.sum()), float(np.abs(rs[0]["peer"] - rs[0]["nccl"]).max()))
+    assert abs(float(rs[0]["peer_sq"]) - float(rs[0]["nccl_sq"])) <= 1e-5 * float(rs[0]["nccl_sq"])

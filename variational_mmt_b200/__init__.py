@@ -16,7 +16,7 @@ from .modules import (Embeddings, LSTM, GlobalAttention, Normal, LocationLayer, 
                       GlobalInferenceNetwork, GlobalFullInferenceNetwork, ImageGlobalInferenceNetwork)
 from .ops import manual_seed
 from .graph import GraphedTrainStep
-from . import translate, distributed
+from . import translate, distributed, io
 from .translate import TranslatorMultimodalVI, GNMTGlobalScorer
 
 __version__ = "0.1.0"

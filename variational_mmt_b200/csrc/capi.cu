@@ -67,6 +67,13 @@ extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float*
   VMMT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dims");
   VMMT_REQUIRE(A && B && C, "gemm: null operand");
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool log_calls = getenv("VMMT_GEMM_LOG") != nullptr;      // debugging: which path each shape takes
+  if (log_calls)
+    fprintf(stderr, "[vmmt_gemm] M=%d N=%d K=%d lda=%lld(%s) ldb=%lld(%s) ldc=%lld bias=%d act=%d acc=%d -> %s\n", M, N, K,
+            (long long)lda, a_kmajor ? "k" : "mn", (long long)ldb, b_kmajor ? "k" : "mn", (long long)ldc, bias != nullptr,
+            act, accumulate,
+            (vmmt_get_gemm_mode() == 0 && vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K))
+                ? "tcgen05" : "simt");
   if (vmmt_get_gemm_mode() == 0 &&
       vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K)) {
     return vmmt_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);

@@ -59,31 +59,45 @@ row_lse_kernel(const float* __restrict__ logits, const int64_t* __restrict__ tar
 }
 
 // fused path: combine the per-tile partials {max, sumexp, best, besti} of a row -> lse, row statistics
-__global__ void lse_combine_kernel(const float4* __restrict__ part, const float* __restrict__ tgt_logit,
-                                   const int64_t* __restrict__ target, int64_t pad, int M, int ntile,
-                                   float* __restrict__ lse, float* __restrict__ rowstat) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+lse_combine_kernel(const float4* __restrict__ part, const float* __restrict__ tgt_logit,
+                   const int64_t* __restrict__ target, int64_t pad, int M, int ntile,
+                   float* __restrict__ lse, float* __restrict__ rowstat) {
+  // one warp per row: lane l folds tiles l, l+32, ... (online rescaling), then a fixed-order shuffle tree
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  float mx = -INFINITY, bestv = -INFINITY;
+  float mx = -INFINITY, s = 0.f, bestv = -INFINITY;
   int besti = 0x7fffffff;
-  for (int t = 0; t < ntile; ++t) {
-    const float4 p = part[(size_t)t * M + row];
-    mx = fmaxf(mx, p.x);
+  for (int t = lane; t < ntile; t += 32) {
+    const float4 p = __ldg(part + (size_t)t * M + row);
+    const float nm = fmaxf(mx, p.x);
+    s = s * __expf(mx - nm) + p.y * __expf(p.x - nm);       // mx = -inf, s = 0 on the first tile: 0 * exp(-inf) = 0
+    mx = nm;
     const int bi = __float_as_int(p.w);
     if (p.z > bestv || (p.z == bestv && bi < besti)) { bestv = p.z; besti = bi; }
   }
-  float s = 0.f;
-  for (int t = 0; t < ntile; ++t) {
-    const float4 p = part[(size_t)t * M + row];
-    s += p.y * expf(p.x - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float obv = __shfl_xor_sync(0xffffffffu, bestv, o);
+    const int obi = __shfl_xor_sync(0xffffffffu, besti, o);
+    const float nm = fmaxf(mx, omx);
+    const float a = (mx == -INFINITY) ? 0.f : s * __expf(mx - nm);
+    const float b = (omx == -INFINITY) ? 0.f : os * __expf(omx - nm);
+    s = a + b;
+    mx = nm;
+    if (obv > bestv || (obv == bestv && obi < besti)) { bestv = obv; besti = obi; }
   }
-  const float Lr = mx + logf(s);
-  lse[row] = Lr;
-  const int64_t tg = target[row];
-  const bool on = tg != pad;
-  rowstat[row * 3 + 0] = on ? (Lr - tgt_logit[row]) : 0.f;
-  rowstat[row * 3 + 1] = on ? 1.f : 0.f;
-  rowstat[row * 3 + 2] = (on && besti == (int)tg) ? 1.f : 0.f;
+  if (lane == 0) {
+    const float Lr = mx + logf(s);
+    lse[row] = Lr;
+    const int64_t tg = target[row];
+    const bool on = tg != pad;
+    rowstat[row * 3 + 0] = on ? (Lr - tgt_logit[row]) : 0.f;
+    rowstat[row * 3 + 1] = on ? 1.f : 0.f;
+    rowstat[row * 3 + 2] = (on && besti == (int)tg) ? 1.f : 0.f;
+  }
 }
 
 // deterministic single-block reduction of the per-row statistics
@@ -150,7 +164,7 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
     VmmtGenEpi epi{1, part, tgt_logit, target, nullptr, nullptr, 1.0f, (long long)pad_idx};
     rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, (cudaStream_t)stream);
     if (rc) return rc;
-    lse_combine_kernel<<<ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(
+    lse_combine_kernel<<<ceil_div(M, 4), 128, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(part), tgt_logit, target, pad_idx, M, ntile, lse, rowstat);
     rc = vmmt_check_launch("lse_combine");
     if (rc) return rc;

@@ -2,5 +2,6 @@
 onmt/translate/Beam.py) with the beam bookkeeping on the device."""
 from .Beam import GNMTGlobalScorer
 from .TranslatorMultimodalVI import TranslatorMultimodalVI
+from .validation import translate_dataset
 
-__all__ = ["TranslatorMultimodalVI", "GNMTGlobalScorer"]
+__all__ = ["TranslatorMultimodalVI", "GNMTGlobalScorer", "translate_dataset"]
