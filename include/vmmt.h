@@ -42,6 +42,14 @@ int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t
               float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
               void* stream);
 
+/* C[M,N] = act(A1 B1^T + A2 B2^T + bias): two operand pairs ([rows,K] row-major, the nn.Linear layout) contracted into one
+ * accumulator in one launch.  Replaces the pairs of nn.Linear-on-a-concatenation the reference spells with torch.cat:
+ * the LSTM cell's x W_ih^T + h W_hh^T (nn.LSTM, VI_Model1.py:106, one decode step) and linear_out([c ; q])
+ * (GlobalAttention.py:187-190). */
+int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, int64_t ldb1, int K1, const float* A2, int64_t lda2,
+                   const float* B2, int64_t ldb2, int K2, float* C, int64_t ldc, int M, int N, const float* bias, int act,
+                   void* stream);
+
 /* Embedding gather / dense scatter-add (Embeddings.py:169-188; nn.Embedding padding_idx row gets no grad). */
 int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int E, float* out, void* stream);
 int vmmt_embedding_bwd(const int64_t* idx, int64_t n, const float* dout, int E, int64_t pad_idx,
@@ -156,6 +164,15 @@ int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H
 int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H, int V,
                             float* out /*[M,V]*/, float* lse_ws /*[M]*/, void* stream);
 
+/* Beam-search form of the generator (TranslatorMultimodalVI.py:199 `self.model.generator.forward(dec_out)` followed by
+ * Beam.advance's topk over beam x vocabulary, Beam.py:64-104): the GEMM epilogue keeps, per row and 128-column tile,
+ * {max, sum exp} and the tile's K best logits; the [M,V] log-prob matrix is never written.  Requires the tensor-core
+ * GEMM (vmmt_generator_topk_supported); otherwise use vmmt_generator_logprobs + vmmt_beam_advance. */
+size_t vmmt_generator_topk_workspace_bytes(int M, int V, int K);
+int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V);
+int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, int H, int V, int K, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ---- optimiser: global-norm clip + Adam on flat buffers (Optim.py:69-70,94-96) */
 size_t vmmt_sqnorm_workspace_bytes(void);
 int vmmt_sqnorm(const float* g, int64_t n, float* out1, int accumulate, void* workspace, void* stream);
@@ -195,6 +212,11 @@ int vmmt_beam_advance(const float* logp, int B, int K, int V, int step, const in
                       int32_t* prev_cur, int64_t eos, float* scores,
                       int64_t* next_ys, int32_t* prev_ks, float* fin_score, int32_t* fin_t, int32_t* fin_k,
                       int32_t* n_fin, int32_t* done, int32_t* n_active, void* stream);
+/* same step on the workspace vmmt_generator_topk(M = K*B rows, K candidates per tile) left behind. */
+int vmmt_beam_advance_topk(const void* gen_workspace, int B, int K, int V, int step, const int64_t* step_dev,
+                           int64_t* tok_cur, int32_t* prev_cur, int64_t eos, float* scores, int64_t* next_ys,
+                           int32_t* prev_ks, float* fin_score, int32_t* fin_t, int32_t* fin_k, int32_t* n_fin,
+                           int32_t* done, int32_t* n_active, void* stream);
 /* hist[*step_dev][0:n] = cur[0:n]: the step's attention rows into the history the hypotheses are read from. */
 int vmmt_beam_record(const float* cur, float* hist, const int64_t* step_dev, int64_t n, void* stream);
 int vmmt_beam_reorder(const float* src, float* dst, const int32_t* prev_k_step, const int32_t* done, int L,

@@ -50,6 +50,18 @@ def check_gemm(mode_tol=1e-5):
     c = c0.clone()
     ops.gemm(a, bv, c, M, N, K, act=2, accumulate=2)
     out.append(("gemm accumulate=2 tanh", _rel(c, torch.tanh(c0.double() + a.double() @ bv.double().t())), mode_tol))
+    # two operand pairs into one accumulator (x W_ih^T + h W_hh^T of a decode step; linear_out([c ; q])):
+    # ragged K tails of both pairs, strided weight slices, skinny and tiny shapes (the tiny one takes the fallback)
+    for (M, N, K1, K2, act, fn) in [(1250, 2000, 500, 500, 0, lambda v: v), (1250, 500, 500, 500, 2, torch.tanh),
+                                    (77, 130, 100, 68, 1, F.relu), (5, 256, 64, 64, 0, lambda v: v),
+                                    (3, 7, 5, 9, 2, torch.tanh)]:
+        a1, a2 = _r(M, K1, seed=8), _r(M, K2, seed=9)
+        w = _r(N, K1 + K2, seed=10)                         # one [N, K1+K2] weight, used as two column slices
+        bias = _r(N, seed=11)
+        c = torch.empty(M, N, device=DEV)
+        ops.gemm_dual(a1, w[:, :K1], a2, w[:, K1:], c, M, N, K1, K2, bias=bias, act=act)
+        ref = fn(torch.cat([a1, a2], 1).double() @ w.double().t() + bias.double())
+        out.append((f"gemm_dual {M}x{N}x({K1}+{K2}) act={act}", _rel(c, ref), 2 * mode_tol))   # K1+K2 terms of TF32 rounding
     return out
 
 

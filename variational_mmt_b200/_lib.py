@@ -43,6 +43,7 @@ SIGNATURES = {
     "vmmt_set_gemm_mode": (None, [I]),
     "vmmt_get_gemm_mode": (I, []),
     "vmmt_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P]),
+    "vmmt_gemm_dual": (I, [P, L, P, L, I, P, L, P, L, I, P, L, I, I, P, I, P]),
     "vmmt_embedding_fwd": (I, [P, L, P, I, P, P]),
     "vmmt_embedding_bwd": (I, [P, L, P, I, L, P, P]),
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
@@ -72,6 +73,9 @@ SIGNATURES = {
     "vmmt_generator_nll_bwd": (I, [P, P, P, P, L, P, P, F, I, I, I, P, P, P, P, SZ, P]),
     "vmmt_generator_nll_wgrad": (I, [P, P, I, I, I, P, P, P]),
     "vmmt_generator_logprobs": (I, [P, P, P, I, I, I, P, P, P]),
+    "vmmt_generator_topk_workspace_bytes": (SZ, [I, I, I]),
+    "vmmt_generator_topk_supported": (I, [P, P, I, I, I]),
+    "vmmt_generator_topk": (I, [P, P, P, I, I, I, I, P, SZ, P]),
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),
     "vmmt_adam_clip_step": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),
@@ -86,6 +90,7 @@ SIGNATURES = {
     "vmmt_peer_slice": (L, [L, I, I, C.POINTER(L), C.POINTER(L)]),
     "vmmt_peer_adam_step": (I, [P, SZ, SZ, I, I, L, P, P, P, P, F, F, F, F, F, L, P, P]),
     "vmmt_beam_advance": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
+    "vmmt_beam_advance_topk": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
     "vmmt_beam_record": (I, [P, P, P, L, P]),
     "vmmt_beam_reorder": (I, [P, P, P, P, I, I, I, I, P]),
 }

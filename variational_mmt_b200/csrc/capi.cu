@@ -80,3 +80,22 @@ extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float*
   }
   return vmmt_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);
 }
+
+// C = act(A1 B1^T + A2 B2^T + bias): two K-major operand pairs contracted into ONE accumulator (one launch, one
+// epilogue).  Falls back to two vmmt_gemm calls when the tensor-core kernel does not apply.
+extern "C" int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, int64_t ldb1, int K1,
+                              const float* A2, int64_t lda2, const float* B2, int64_t ldb2, int K2, float* C,
+                              int64_t ldc, int M, int N, const float* bias, int act, void* stream) {
+  VMMT_REQUIRE(M >= 0 && N >= 0 && K1 >= 1 && K2 >= 1, "gemm_dual: bad dims");
+  VMMT_REQUIRE(A1 && B1 && A2 && B2 && C, "gemm_dual: null operand");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vmmt_get_gemm_mode() == 0 && vmmt_gemm_tc_eligible(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1) &&
+      vmmt_gemm_tc_eligible(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2)) {
+    // each pair has its own tensor maps, so a ragged K tail of either is zero-filled by the TMA independently
+    VmmtGemmSecond second{A2, lda2, B2, ldb2, K2};
+    return vmmt_gemm_tc_dual(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, act, 0, nullptr, &second, s);
+  }
+  int rc = vmmt_gemm(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, VMMT_ACT_NONE, 0, stream);
+  if (rc) return rc;
+  return vmmt_gemm(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2, nullptr, act, act == VMMT_ACT_NONE ? 1 : 2, stream);
+}

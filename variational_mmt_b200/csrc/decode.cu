@@ -18,52 +18,15 @@ __device__ __forceinline__ bool better(float v, int i, float w, int j) {
   return v > w || (v == w && i < j);
 }
 
-// One CTA per sentence.  logp [K*B, V] -> top-K of the flattened [K*V] candidate scores.
-__global__ void __launch_bounds__(256)
-beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int step_host,
-                    const int64_t* __restrict__ step_dev,   // device-resident step index (CUDA-graph replays) or null
-                    int64_t* __restrict__ tok_cur,          // [K,B] newest tokens (fixed address) or null
-                    int32_t* __restrict__ prev_cur,         // [K,B] newest back pointers (fixed address) or null
-                    int64_t eos,
-                    float* __restrict__ scores,        // [B,K] running hypothesis scores (in/out)
-                    int64_t* __restrict__ next_ys,     // [Lmax+1, K, B] tokens; slice `step` is the input
-                    int32_t* __restrict__ prev_ks,     // [Lmax, K, B] back pointers
-                    float* __restrict__ fin_score,     // [B] best finished score
-                    int32_t* __restrict__ fin_t, int32_t* __restrict__ fin_k,   // [B]
-                    int32_t* __restrict__ n_fin, int32_t* __restrict__ done,    // [B]
-                    int32_t* __restrict__ n_active) {
-  const int b = blockIdx.x;
-  const int step = step_dev ? (int)*step_dev : step_host;
-  if (done[b]) {
-    if (threadIdx.x < K && prev_cur) prev_cur[threadIdx.x * B + b] = threadIdx.x;   // frozen sentence: identity reorder
-    return;
-  }
-  __shared__ Cand cand[256 * KMAX];
-  __shared__ Cand best[KMAX];
-  __shared__ float rv[8];
-  __shared__ int ri[8], rp[8];
+// Shared tail of the two advance kernels: block-wide top-K over the threads' local lists, then Beam.advance's
+// bookkeeping for sentence b (scores, back pointers, tokens, finished hypotheses, done flag).
+__device__ __forceinline__ void beam_select_and_update(
+    Cand (&loc)[KMAX], Cand* cand, Cand* best, float* rv, int* ri, int* rp, int b, int B, int K, int V, int step,
+    int64_t* __restrict__ tok_cur, int32_t* __restrict__ prev_cur, int64_t eos, float* __restrict__ scores,
+    int64_t* __restrict__ next_ys, int32_t* __restrict__ prev_ks, float* __restrict__ fin_score,
+    int32_t* __restrict__ fin_t, int32_t* __restrict__ fin_k, int32_t* __restrict__ n_fin, int32_t* __restrict__ done,
+    int32_t* __restrict__ n_active) {
   const int tid = threadIdx.x;
-  Cand loc[KMAX];
-#pragma unroll
-  for (int q = 0; q < KMAX; ++q) { loc[q].v = -INFINITY; loc[q].i = 0x7fffffff; }
-  const int nbeam = (step == 0) ? 1 : K;               // Beam.py:93-94: first step uses beam row 0 only
-  for (int k = 0; k < nbeam; ++k) {
-    const float base = (step == 0) ? 0.f : scores[b * K + k];
-    const bool dead = step > 0 && next_ys[((size_t)step * K + k) * B + b] == eos;   // Beam.py:89-92
-    const float* row = logp + ((size_t)k * B + b) * V;
-    for (int j = tid; j < V; j += blockDim.x) {
-      const float v = dead ? -1e20f : row[j] + base;
-      const int id = k * V + j;
-      if (better(v, id, loc[K - 1].v, loc[K - 1].i)) {
-        loc[K - 1].v = v; loc[K - 1].i = id;
-#pragma unroll
-        for (int q = KMAX - 1; q > 0; --q)
-          if (q < K && better(loc[q].v, loc[q].i, loc[q - 1].v, loc[q - 1].i)) {
-            const Cand tmp = loc[q]; loc[q] = loc[q - 1]; loc[q - 1] = tmp;
-          }
-      }
-    }
-  }
   for (int q = 0; q < K; ++q) cand[tid * KMAX + q] = loc[q];
   __syncthreads();
   // K rounds of block-wide arg-max over the 256*K local winners
@@ -113,6 +76,137 @@ beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int ste
   }
 }
 
+// One CTA per sentence.  logp [K*B, V] -> top-K of the flattened [K*V] candidate scores.
+__global__ void __launch_bounds__(256)
+beam_advance_kernel(const float* __restrict__ logp, int B, int K, int V, int step_host,
+                    const int64_t* __restrict__ step_dev,   // device-resident step index (CUDA-graph replays) or null
+                    int64_t* __restrict__ tok_cur,          // [K,B] newest tokens (fixed address) or null
+                    int32_t* __restrict__ prev_cur,         // [K,B] newest back pointers (fixed address) or null
+                    int64_t eos,
+                    float* __restrict__ scores,        // [B,K] running hypothesis scores (in/out)
+                    int64_t* __restrict__ next_ys,     // [Lmax+1, K, B] tokens; slice `step` is the input
+                    int32_t* __restrict__ prev_ks,     // [Lmax, K, B] back pointers
+                    float* __restrict__ fin_score,     // [B] best finished score
+                    int32_t* __restrict__ fin_t, int32_t* __restrict__ fin_k,   // [B]
+                    int32_t* __restrict__ n_fin, int32_t* __restrict__ done,    // [B]
+                    int32_t* __restrict__ n_active) {
+  const int b = blockIdx.x;
+  const int step = step_dev ? (int)*step_dev : step_host;
+  if (done[b]) {
+    if (threadIdx.x < K && prev_cur) prev_cur[threadIdx.x * B + b] = threadIdx.x;   // frozen sentence: identity reorder
+    return;
+  }
+  __shared__ Cand cand[256 * KMAX];
+  __shared__ Cand best[KMAX];
+  __shared__ float rv[8];
+  __shared__ int ri[8], rp[8];
+  const int tid = threadIdx.x;
+  Cand loc[KMAX];
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q) { loc[q].v = -INFINITY; loc[q].i = 0x7fffffff; }
+  const int nbeam = (step == 0) ? 1 : K;               // Beam.py:93-94: first step uses beam row 0 only
+  for (int k = 0; k < nbeam; ++k) {
+    const float base = (step == 0) ? 0.f : scores[b * K + k];
+    const bool dead = step > 0 && next_ys[((size_t)step * K + k) * B + b] == eos;   // Beam.py:89-92
+    const float* row = logp + ((size_t)k * B + b) * V;
+    for (int j = tid; j < V; j += blockDim.x) {
+      const float v = dead ? -1e20f : row[j] + base;
+      const int id = k * V + j;
+      if (better(v, id, loc[K - 1].v, loc[K - 1].i)) {
+        loc[K - 1].v = v; loc[K - 1].i = id;
+#pragma unroll
+        for (int q = KMAX - 1; q > 0; --q)
+          if (q < K && better(loc[q].v, loc[q].i, loc[q - 1].v, loc[q - 1].i)) {
+            const Cand tmp = loc[q]; loc[q] = loc[q - 1]; loc[q - 1] = tmp;
+          }
+      }
+    }
+  }
+  beam_select_and_update(loc, cand, best, rv, ri, rp, b, B, K, V, step, tok_cur, prev_cur, eos, scores, next_ys,
+                         prev_ks, fin_score, fin_t, fin_k, n_fin, done, n_active);
+}
+
+// Fused-generator variant: the generator GEMM's epilogue (gemm_tc.cu, mode 3) left, per row and 128-column tile,
+// {max, sum exp} and the tile's best logits.  One CTA per sentence: warp k combines the tile partials of beam row k
+// into its log-sum-exp, then the K * ntile * kc candidates (logit - lse + hypothesis score) go through the same
+// selection as above.  The global top-K of a [K, V] score matrix is contained in the union of the per-tile top-K
+// lists, so the result is the one beam_advance_kernel finds on the materialised log-probs.
+__global__ void __launch_bounds__(256)
+beam_advance_topk_kernel(const float2* __restrict__ tile_lse, const float2* __restrict__ tile_cand, int ntile, int kc,
+                         int B, int K, int V, int step_host, const int64_t* __restrict__ step_dev,
+                         int64_t* __restrict__ tok_cur, int32_t* __restrict__ prev_cur, int64_t eos,
+                         float* __restrict__ scores, int64_t* __restrict__ next_ys, int32_t* __restrict__ prev_ks,
+                         float* __restrict__ fin_score, int32_t* __restrict__ fin_t, int32_t* __restrict__ fin_k,
+                         int32_t* __restrict__ n_fin, int32_t* __restrict__ done, int32_t* __restrict__ n_active) {
+  const int b = blockIdx.x;
+  const int step = step_dev ? (int)*step_dev : step_host;
+  if (done[b]) {
+    if (threadIdx.x < K && prev_cur) prev_cur[threadIdx.x * B + b] = threadIdx.x;
+    return;
+  }
+  __shared__ Cand cand[256 * KMAX];
+  __shared__ Cand best[KMAX];
+  __shared__ float rv[8];
+  __shared__ int ri[8], rp[8];
+  __shared__ float lse_s[KMAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = K * B;
+  const int nbeam = (step == 0) ? 1 : K;
+  if (warp < nbeam) {                                    // K <= 8 = warps per CTA
+    const int row = warp * B + b;
+    float mx = -INFINITY, sm = 0.f;
+    for (int t = lane; t < ntile; t += 32) {
+      const float2 p = tile_lse[(size_t)t * M + row];
+      const float nm = fmaxf(mx, p.x);
+      sm = sm * __expf(mx - nm) + p.y * __expf(p.x - nm);
+      mx = nm;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float omx = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o);
+      const float nm = fmaxf(mx, omx);
+      const float a = (mx == -INFINITY) ? 0.f : sm * __expf(mx - nm);
+      const float c = (omx == -INFINITY) ? 0.f : os * __expf(omx - nm);
+      sm = a + c;
+      mx = nm;
+    }
+    if (lane == 0) lse_s[warp] = mx + logf(sm);
+  }
+  __syncthreads();
+  Cand loc[KMAX];
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q) { loc[q].v = -INFINITY; loc[q].i = 0x7fffffff; }
+  auto push = [&](float v, int id) {
+    if (better(v, id, loc[K - 1].v, loc[K - 1].i)) {
+      loc[K - 1].v = v; loc[K - 1].i = id;
+#pragma unroll
+      for (int q = KMAX - 1; q > 0; --q)
+        if (q < K && better(loc[q].v, loc[q].i, loc[q - 1].v, loc[q - 1].i)) {
+          const Cand tmp = loc[q]; loc[q] = loc[q - 1]; loc[q - 1] = tmp;
+        }
+    }
+  };
+  const int per_row = ntile * kc;
+  for (int k = 0; k < nbeam; ++k) {
+    const bool dead = step > 0 && next_ys[((size_t)step * K + k) * B + b] == eos;     // Beam.py:89-92
+    if (dead) {                                           // every column scores -1e20: the K lowest columns win
+      if (tid < K && tid < V) push(-1e20f, k * V + tid);
+      continue;
+    }
+    const float base = (step == 0) ? 0.f : scores[b * K + k];
+    const float lse = lse_s[k];
+    const int row = k * B + b;
+    for (int i = tid; i < per_row; i += blockDim.x) {
+      const int t = i / kc, q = i - t * kc;
+      const float2 c = tile_cand[((size_t)t * M + row) * kc + q];
+      const int col = __float_as_int(c.y);
+      if (col != 0x7fffffff) push((c.x - lse) + base, k * V + col);
+    }
+  }
+  beam_select_and_update(loc, cand, best, rv, ri, rp, b, B, K, V, step, tok_cur, prev_cur, eos, scores, next_ys,
+                         prev_ks, fin_score, fin_t, fin_k, n_fin, done, n_active);
+}
+
 // new[l, k*B+b, :] = old[l, prev_k[k,b]*B + b, :]   (DecoderState.beam_update)
 __global__ void beam_reorder_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                     const int32_t* __restrict__ prev_k, const int32_t* __restrict__ done,
@@ -159,6 +253,22 @@ extern "C" int vmmt_beam_advance(const float* logp, int B, int K, int V, int ste
                                                           scores, next_ys, prev_ks, fin_score, fin_t, fin_k,
                                                           n_fin, done, n_active);
   return vmmt_check_launch("beam_advance");
+}
+
+extern "C" int vmmt_beam_advance_topk(const void* gen_workspace, int B, int K, int V, int step,
+                                      const int64_t* step_dev, int64_t* tok_cur, int32_t* prev_cur, int64_t eos,
+                                      float* scores, int64_t* next_ys, int32_t* prev_ks, float* fin_score,
+                                      int32_t* fin_t, int32_t* fin_k, int32_t* n_fin, int32_t* done,
+                                      int32_t* n_active, void* stream) {
+  VMMT_REQUIRE(K >= 1 && K <= KMAX, "beam_advance_topk: beam size %d outside [1,%d]", K, KMAX);
+  const int ntile = ceil_div(V, 128);
+  const size_t M = (size_t)K * B;
+  const float2* tile_lse = (const float2*)gen_workspace;           // layout of vmmt_generator_topk
+  const float2* tile_cand = tile_lse + (size_t)ntile * M;
+  beam_advance_topk_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(tile_lse, tile_cand, ntile, K, B, K, V, step, step_dev,
+                                                               tok_cur, prev_cur, eos, scores, next_ys, prev_ks,
+                                                               fin_score, fin_t, fin_k, n_fin, done, n_active);
+  return vmmt_check_launch("beam_advance_topk");
 }
 
 // hist[step][r][:] = cur[r][:]  (attention rows of the current step into the per-step history)

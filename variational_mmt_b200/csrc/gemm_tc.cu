@@ -138,6 +138,7 @@ struct GemmArgs {
   int kb_per_split;      // k-blocks (of BK) per gridDim.z slice
   int tma_store;         // 1: epilogue stores / reduces through the tmC tensor map
   int dbg;
+  int nkb2;             // k-blocks of the optional second operand pair (C = A B^T + A2 B2^T, both K-major), else 0
   long long* trace;     // debug: per-CTA timeline (8 slots), or null
   // fused generator epilogues (vmmt_internal.h: VmmtGenEpi): 0 none, 1 per-row log-sum-exp partials instead of C,
   // 2 C = softmax-NLL gradient of the tile
@@ -149,6 +150,9 @@ struct GemmArgs {
   const float* gscale;          // mode 2: device scalar or null
   float scale;                  // mode 2
   long long pad;                // mode 2: ignored target id
+  int topk;                     // mode 3
+  float2* tile_lse;             // mode 3: [tiles_n][M] {max, sum exp}
+  float2* tile_cand;            // mode 3: [tiles_n][M][topk] {logit, column}
 };
 
 template <int ACT>
@@ -246,6 +250,62 @@ __device__ __forceinline__ void epilogue_lse(const GemmArgs& g, uint32_t tmem_ba
   }
 }
 
+// Beam-search generator: per row of the tile {max, sum exp} and the tile's top-K logits (value, column), best first;
+// ties keep the lowest column (the rule of beam_advance_kernel / the CPU oracle).  Nothing of size M x N is written.
+template <int BN, int KL>      // KL = compile-time list length (>= g.topk): 5 covers the published beam size, 8 the maximum
+__device__ __forceinline__ void epilogue_topk(const GemmArgs& g, uint32_t tmem_base, const float* bias_s, int q, int lane,
+                                              int m0, int n0) {
+  const int row = m0 + 32 * q + lane;
+  const int K = g.topk;
+  float mx = -INFINITY, sum = 0.f;
+  float bv[KL];
+  int bi[KL];
+#pragma unroll
+  for (int k = 0; k < KL; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= g.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
+    float x[32], cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      x[j] = (col0 + j < g.N) ? __uint_as_float(v[j]) + bias_s[c * 32 + j] : -INFINITY;
+      cm = fmaxf(cm, x[j]);
+    }
+    // the list always holds KL entries (compile-time register indices); the first K are written out
+    if (cm > bv[KL - 1]) {                                        // some column of the chunk enters the list
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (x[j] > bv[KL - 1]) {                                  // ascending columns + strict '>' keep the lowest column
+          bv[KL - 1] = x[j]; bi[KL - 1] = col0 + j;
+#pragma unroll
+          for (int k = KL - 1; k > 0; --k)
+            if (bv[k] > bv[k - 1]) {
+              const float tv = bv[k]; bv[k] = bv[k - 1]; bv[k - 1] = tv;
+              const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+            }
+        }
+      }
+    }
+    const float nm = fmaxf(mx, cm);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += __expf(x[j] - nm);
+    sum = sum * __expf(mx - nm) + s;
+    mx = nm;
+  }
+  if (row < g.M) {
+    const size_t t = (size_t)(n0 / BN) * g.M + row;
+    g.tile_lse[t] = make_float2(mx, sum);
+    float2* dst = g.tile_cand + t * K;
+#pragma unroll
+    for (int k = 0; k < KL; ++k)
+      if (k < K) dst[k] = make_float2(bv[k], __int_as_float(bi[k]));
+  }
+}
+
 template <int BN, int ACT, bool DL = false>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUtensorMap* tmC, uint32_t tmem_base,
                                                   uint32_t stage_u32, const float* bias_s, int q, int lane, int m0,
@@ -310,7 +370,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUten
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB2, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE = b_stage_bytes(BN);
   constexpr int STAGE = A_STAGE_BYTES + B_STAGE;
@@ -343,13 +404,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nkb_total = (g.K + BK - 1) / BK;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + g.kb_per_split);
-  const int nkb = (g.dbg & 2) ? 0 : kb1 - kb0;           // >= 1 by construction of the grid
+  const int nkb1 = kb1 - kb0;                            // k-blocks of the first operand pair in this CTA
+  const int nkb = (g.dbg & 2) ? 0 : nkb1 + g.nkb2;       // >= 1 by construction of the grid
 
   if (threadIdx.x == 0) trace_mark(g.trace, 0);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (g.nkb2) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -380,20 +446,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(empty0 + 8 * s, ph ^ 1);
       const uint32_t fb = full0 + 8 * s;
       const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
-      const int k = (kb0 + i) * BK;
+      const bool second = i >= nkb1;                               // k-blocks of the second operand pair follow the first
+      const int k = second ? (i - nkb1) * BK : (kb0 + i) * BK;
+      const CUtensorMap* pa = second ? &tmA2 : &tmA;
+      const CUtensorMap* pb = second ? &tmB2 : &tmB;
       if (leader) {
         mbar_expect_tx(fb, STAGE);
         if (!A_MN) {
-          tma_load_2d(sa, &tmA, k, m0, fb);                        // box {32 k, 128 rows}
+          tma_load_2d(sa, pa, k, m0, fb);                          // box {32 k, 128 rows}
         } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, m0 + 32 * j, k, fb);   // box {32 m, 32 k}
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), pa, m0 + 32 * j, k, fb);   // box {32 m, 32 k}
         }
         if (!B_MN) {
-          tma_load_2d(sb, &tmB, k, n0, fb);                        // box {32 k, BN rows}
+          tma_load_2d(sb, pb, k, n0, fb);                          // box {32 k, BN rows}
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, n0 + 32 * j, k, fb);
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), pb, n0 + 32 * j, k, fb);
         }
       }
       __syncwarp();
@@ -428,7 +497,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 64) trace_mark(g.trace, 4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int mode = (gridDim.z > 1) ? 3 : g.accumulate;        // 0 store, 1 C += v, 2 act(C + v), 3 atomic
-    if ((g.tma_store && mode != 2) || g.epi_mode == 1) {
+    if ((g.tma_store && mode != 2) || g.epi_mode == 1 || g.epi_mode == 3) {
       float* bias_s = epi + EPI_WARPS * 2 * 1024;                // [BN] staged once per tile by the 4 warps
       for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS)
         bias_s[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
@@ -436,6 +505,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t st = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
       if (g.epi_mode == 1) {
         epilogue_lse<BN>(g, tmem_base, bias_s, q, lane, m0, n0);
+      } else if (g.epi_mode == 3) {
+        if (g.topk <= 5) epilogue_topk<BN, 5>(g, tmem_base, bias_s, q, lane, m0, n0);
+        else epilogue_topk<BN, VMMT_TOPK_MAX>(g, tmem_base, bias_s, q, lane, m0, n0);
       } else if (g.epi_mode == 2) {
         epilogue_tile_tma<BN, VMMT_ACT_NONE, true>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode);
       } else
@@ -524,9 +596,10 @@ int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int6
   return VMMT_OK;
 }
 
+struct Maps { CUtensorMap a, b, c, a2, b2; };
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g, dim3 grid,
-           cudaStream_t s) {
+int launch(const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
   auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
   static bool attr_done = false;        // per instantiation
   constexpr size_t smem = smem_bytes(BN, STAGES);
@@ -534,17 +607,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     VMMT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  kern<<<grid, THREADS, smem, s>>>(ta, tb, tc, g);
+  kern<<<grid, THREADS, smem, s>>>(m.a, m.b, m.c, m.a2, m.b2, g);
   return vmmt_check_launch("gemm_tf32_kernel");
 }
 
 template <int BN, int STAGES>
-int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                 const GemmArgs& g, dim3 grid, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(ta, tb, tc, g, grid, s);
-  if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(ta, tb, tc, g, grid, s);
-  if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(ta, tb, tc, g, grid, s);
-  return launch<BN, STAGES, true, true>(ta, tb, tc, g, grid, s);
+int launch_major(bool a_mn, bool b_mn, const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(m, g, grid, s);
+  if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(m, g, grid, s);
+  if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(m, g, grid, s);
+  return launch<BN, STAGES, true, true>(m, g, grid, s);
 }
 
 }  // namespace
@@ -570,14 +642,22 @@ int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int6
 int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
                     int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
                     const VmmtGenEpi* epi, cudaStream_t s) {
+  return vmmt_gemm_tc_dual(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, epi, nullptr, s);
+}
+
+int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
+                      int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
+                      const VmmtGenEpi* epi, const VmmtGemmSecond* second, cudaStream_t s) {
   const bool a_mn = !a_kmajor, b_mn = !b_kmajor;
   const int nsm = vmmt_num_sms();
   const int tiles_m = ceil_div(M, BM);
-  const int nkb = ceil_div(K, BK);
+  const int nkb2 = second ? ceil_div(second->K2, BK) : 0;
+  if (second && (a_mn || b_mn)) return VMMT_EINVAL;            // the second pair shares the K-major instantiation
+  const int nkb = ceil_div(K, BK) + nkb2;                       // k-blocks per output tile (cost model); split-K only without a second pair
   // (tile width, split-K) from a small cost model in SM cycles: a CTA costs a fixed prologue + epilogue plus
   // its k-blocks; 128-wide tiles run one CTA per SM (shared-memory-bandwidth bound, ~450 cycles per k-block),
   // 64-wide tiles two per SM; split-K needs a linear epilogue (an activation is applied by a finishing pass)
-  const bool can_split = epi == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
+  const bool can_split = epi == nullptr && second == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
   int BN = 128, splits = 1;
   double best = 1e30;
   for (int bn = (epi ? 128 : 64); bn <= 128; bn *= 2) {
@@ -612,7 +692,7 @@ int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, i
   if (rc) return rc;
   static int dbg = getenv("VMMT_GEMM_DBG") ? atoi(getenv("VMMT_GEMM_DBG")) : 0;
   // C through TMA (store / reduce-add) when its base and pitch are 16-byte aligned; else direct stores
-  const bool lse_mode = epi != nullptr && epi->mode == 1;        // no C at all
+  const bool lse_mode = epi != nullptr && (epi->mode == 1 || epi->mode == 3);        // no C at all
   const int tma_store = (!lse_mode && ((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && accumulate != 2 &&
                          (epi != nullptr || !getenv("VMMT_GEMM_NO_TMA_STORE"))) ? 1 : 0;
   if (epi != nullptr && epi->mode == 2 && !tma_store) return VMMT_EINVAL;   // the gradient epilogue lives in the TMA-store path
@@ -623,8 +703,15 @@ int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, i
   } else {
     tc = ta;
   }
-  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, nullptr,
-             0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0};
+  Maps maps{ta, tb, tc, ta, tb};
+  if (second) {
+    rc = make_map(&maps.a2, second->A2, second->K2, M, second->lda2, BM, false);
+    if (rc) return rc;
+    rc = make_map(&maps.b2, second->B2, second->K2, N, second->ldb2, BN, false);
+    if (rc) return rc;
+  }
+  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, nkb2, nullptr,
+             0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, 0, nullptr, nullptr};
   if (epi) {
     g.epi_mode = epi->mode;
     g.lse_part = reinterpret_cast<float4*>(epi->lse_part);
@@ -634,6 +721,10 @@ int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, i
     g.gscale = epi->gscale;
     g.scale = epi->scale;
     g.pad = epi->pad;
+    g.topk = epi->topk;
+    g.tile_lse = reinterpret_cast<float2*>(epi->tile_lse);
+    g.tile_cand = reinterpret_cast<float2*>(epi->tile_cand);
+    if (epi->mode == 3 && (epi->topk < 1 || epi->topk > VMMT_TOPK_MAX)) return VMMT_EINVAL;
   }
   dim3 grid(ceil_div(N, BN), tiles_m, splits);
   static long long* trace_buf = nullptr;
@@ -661,11 +752,11 @@ int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, i
   } dump{tracing, trace_buf, grid, s, BN};
   static const int deep = getenv("VMMT_GEMM_DEEP") ? atoi(getenv("VMMT_GEMM_DEEP")) : 0;
   if (deep)
-    rc = (BN == 128) ? launch_major<128, 6>(a_mn, b_mn, ta, tb, tc, g, grid, s)
-                     : launch_major<64, 8>(a_mn, b_mn, ta, tb, tc, g, grid, s);
+    rc = (BN == 128) ? launch_major<128, 6>(a_mn, b_mn, maps, g, grid, s)
+                     : launch_major<64, 8>(a_mn, b_mn, maps, g, grid, s);
   else
-    rc = (BN == 128) ? launch_major<128, 5>(a_mn, b_mn, ta, tb, tc, g, grid, s)
-                     : launch_major<64, 3>(a_mn, b_mn, ta, tb, tc, g, grid, s);
+    rc = (BN == 128) ? launch_major<128, 5>(a_mn, b_mn, maps, g, grid, s)
+                     : launch_major<64, 3>(a_mn, b_mn, maps, g, grid, s);
   if (rc) return rc;
   if (finish_act) {
     const int64_t tot = (int64_t)M * N;

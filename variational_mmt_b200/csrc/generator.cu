@@ -236,3 +236,33 @@ extern "C" int vmmt_generator_logprobs(const float* x, const float* W, const flo
   logprob_kernel<<<dim3(ceil_div(V, 256), M), 256, 0, (cudaStream_t)stream>>>(out, lse_ws, V);
   return vmmt_check_launch("logprob");
 }
+
+// ---- beam-search generator: no [M,V] log-prob matrix.  Workspace = [ntile][M] float2 {max, sum exp} followed by
+// [ntile][M][K] float2 {logit, column}; consumed by vmmt_beam_advance_topk (decode.cu).
+extern "C" size_t vmmt_generator_topk_workspace_bytes(int M, int V, int K) {
+  const size_t ntile = (size_t)ceil_div(V, 128);
+  return ntile * (size_t)M * (size_t)(1 + K) * sizeof(float2);
+}
+
+extern "C" int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V) {
+  return (vmmt_get_gemm_mode() == 0 && vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) ? 1 : 0;
+}
+
+extern "C" int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, int H, int V, int K,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  VMMT_REQUIRE(K >= 1 && K <= VMMT_TOPK_MAX, "generator_topk: K = %d outside [1,%d]", K, VMMT_TOPK_MAX);
+  if (workspace_bytes < vmmt_generator_topk_workspace_bytes(M, V, K)) {
+    vmmt_set_error("generator_topk: workspace too small");
+    return VMMT_EWORKSPACE;
+  }
+  VMMT_REQUIRE(vmmt_generator_topk_supported(x, W, M, H, V),
+               "generator_topk: needs the tensor-core GEMM (gemm mode 0, 16-byte aligned operands, H %% 4 == 0, V,H >= 64)");
+  const size_t ntile = (size_t)ceil_div(V, 128);
+  float* tile_lse = (float*)workspace;
+  float* tile_cand = tile_lse + ntile * (size_t)M * 2;
+  VmmtGenEpi epi{3, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0};
+  epi.topk = K;
+  epi.tile_lse = tile_lse;
+  epi.tile_cand = tile_cand;
+  return vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, (cudaStream_t)stream);
+}

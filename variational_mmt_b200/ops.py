@@ -190,6 +190,14 @@ def gemm(a, b, out, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NO
     return out
 
 
+def gemm_dual(a1, b1, a2, b2, out, M, N, K1, K2, bias=None, act=ACT_NONE):
+    """out[M,N] = act(a1 b1^T + a2 b2^T + bias) in one launch (all operands [rows, K] with unit inner stride)."""
+    assert a1.stride(-1) == 1 and b1.stride(-1) == 1 and a2.stride(-1) == 1 and b2.stride(-1) == 1 and out.stride(-1) == 1
+    L.call("vmmt_gemm_dual", fptr(a1), a1.stride(0), fptr(b1), b1.stride(0), K1, fptr(a2), a2.stride(0), fptr(b2),
+           b2.stride(0), K2, fptr(out), out.stride(0), M, N, fptr(bias), act, stream())
+    return out
+
+
 def colsum_acc(a, M, N, out, out2=None):
     L.call("vmmt_colsum_acc", fptr(a), a.stride(0), M, N, fptr(out), fptr(out2), stream())
 

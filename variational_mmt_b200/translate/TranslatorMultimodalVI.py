@@ -59,7 +59,7 @@ class TranslatorMultimodalVI(object):
     # ------------------------------------------------------------------------------------------
     def _buffers(self, B, S, dev):
         """Static device buffers (and the captured step graph) of one (sentences, src_len) bucket."""
-        key = (B, S, str(dev))
+        key = (B, S, str(dev), int(L.lib.vmmt_get_gemm_mode()))
         st = self._buckets.get(key)
         if st is not None:
             self._buckets.move_to_end(key)
@@ -75,8 +75,8 @@ class TranslatorMultimodalVI(object):
         i32 = dict(device=dev, dtype=torch.int32)
         st = _State()
         st.B, st.S, st.R = B, S, R
-        st.ctx = torch.zeros(S, R, H, **f32)
-        st.len_r = torch.zeros(R, device=dev, dtype=torch.int64)
+        st.ctx = torch.zeros(S, B, H, **f32)            # NOT tiled over the beam: the K hypotheses of a sentence share it
+        st.len_b = torch.zeros(B, device=dev, dtype=torch.int64)
         st.zb = torch.zeros(R, 4 * H, **f32)
         st.h, st.c = torch.zeros(nl, R, H, **f32), torch.zeros(nl, R, H, **f32)
         st.h2, st.c2 = torch.zeros_like(st.h), torch.zeros_like(st.c)
@@ -93,7 +93,15 @@ class TranslatorMultimodalVI(object):
         st.align = torch.zeros(R, S, **f32)
         st.emb, st.gpre = torch.zeros(R, E, **f32), torch.zeros(R, 4 * H, **f32)
         st.qp, st.cvec, st.out = (torch.zeros(R, H, **f32) for _ in range(3))
-        st.logp, st.lse = torch.zeros(R, V, **f32), torch.zeros(R, **f32)
+        # generator: with the tensor-core GEMM the epilogue keeps per-tile {max, sum exp, top-K} only; the [R,V] log-prob
+        # matrix exists only on the exact-fp32 (SIMT) parity path
+        st.fused_gen = bool(L.lib.vmmt_generator_topk_supported(fptr(st.out), fptr(model.generator[0].weight), R, H, V))
+        if st.fused_gen:
+            st.gen_ws_bytes = int(L.lib.vmmt_generator_topk_workspace_bytes(R, V, K))
+            st.gen_ws = torch.zeros(st.gen_ws_bytes // 4, **f32)
+            st.logp = st.lse = None
+        else:
+            st.logp, st.lse = torch.zeros(R, V, **f32), torch.zeros(R, **f32)
         st.graph = None
         st.att_host = None
         self._buckets[key] = st
@@ -126,8 +134,7 @@ class TranslatorMultimodalVI(object):
         for l in range(nl):
             w_ih, w_hh = getattr(w, "weight_ih_l%d" % l), getattr(w, "weight_hh_l%d" % l)
             in_dim = E if l == 0 else H
-            ops.gemm(x, w_ih[:, :in_dim], st.gpre, R, 4 * H, in_dim)
-            ops.gemm(st.h[l], w_hh, st.gpre, R, 4 * H, H, accumulate=1)
+            ops.gemm_dual(x, w_ih[:, :in_dim], st.h[l], w_hh, st.gpre, R, 4 * H, in_dim, H)   # x W_ih^T + h W_hh^T
             L.call("vmmt_lstm_cell_fwd", fptr(st.gpre), fptr(getattr(w, "bias_ih_l%d" % l)),
                    fptr(getattr(w, "bias_hh_l%d" % l)), fptr(st.zb) if l == 0 else None, fptr(st.c[l]),
                    fptr(st.h2[l]), fptr(st.c2[l]), R, H, sm)
@@ -138,17 +145,25 @@ class TranslatorMultimodalVI(object):
             q = st.qp
         else:
             q = x
-        L.call("vmmt_attention_fwd", fptr(q), fptr(st.ctx), ptr(st.len_r), fptr(st.align), fptr(st.cvec), 1, R, S, H, sm)
+        # rows are beam-major (row = k*B + b), i.e. q is [K, B, H]: the K hypotheses of sentence b are K "time steps" over
+        # the SAME context column, so the tiled sequence kernel reads ctx[:, b, :] once per sentence, not once per row
+        L.call("vmmt_attention_fwd", fptr(q), fptr(st.ctx), ptr(st.len_b), fptr(st.align), fptr(st.cvec), K, B, S, H, sm)
         L.call("vmmt_beam_record", fptr(st.align), fptr(st.attn_hist), ptr(st.step), R * S, sm)
         w_out = dec.attn.linear_out.weight
-        ops.gemm(st.cvec, w_out[:, :H], st.out, R, H, H)
-        ops.gemm(x, w_out[:, H:], st.out, R, H, H, act=ACT_TANH, accumulate=2)
-        L.call("vmmt_generator_logprobs", fptr(st.out), fptr(gen.weight), fptr(gen.bias), R, H, V, fptr(st.logp),
-               fptr(st.lse), sm)
-        # Beam.advance for every sentence + DecoderState.beam_update (Beam.py:64-123, Models.py:589-594)
-        L.call("vmmt_beam_advance", fptr(st.logp), B, K, V, 0, ptr(st.step), ptr(st.tok_cur), ptr(st.prev_cur),
-               self.eos, fptr(st.scores), ptr(st.next_ys), ptr(st.prev_ks), fptr(st.fin_score), ptr(st.fin_t),
-               ptr(st.fin_k), ptr(st.n_fin), ptr(st.done), ptr(st.n_active), sm)
+        ops.gemm_dual(st.cvec, w_out[:, :H], x, w_out[:, H:], st.out, R, H, H, H, act=ACT_TANH)   # tanh(linear_out([c ; q]))
+        # generator + Beam.advance for every sentence + DecoderState.beam_update (Beam.py:64-123, Models.py:589-594)
+        if st.fused_gen:
+            L.call("vmmt_generator_topk", fptr(st.out), fptr(gen.weight), fptr(gen.bias), R, H, V, K, fptr(st.gen_ws),
+                   st.gen_ws_bytes, sm)
+            L.call("vmmt_beam_advance_topk", fptr(st.gen_ws), B, K, V, 0, ptr(st.step), ptr(st.tok_cur),
+                   ptr(st.prev_cur), self.eos, fptr(st.scores), ptr(st.next_ys), ptr(st.prev_ks), fptr(st.fin_score),
+                   ptr(st.fin_t), ptr(st.fin_k), ptr(st.n_fin), ptr(st.done), ptr(st.n_active), sm)
+        else:
+            L.call("vmmt_generator_logprobs", fptr(st.out), fptr(gen.weight), fptr(gen.bias), R, H, V, fptr(st.logp),
+                   fptr(st.lse), sm)
+            L.call("vmmt_beam_advance", fptr(st.logp), B, K, V, 0, ptr(st.step), ptr(st.tok_cur), ptr(st.prev_cur),
+                   self.eos, fptr(st.scores), ptr(st.next_ys), ptr(st.prev_ks), fptr(st.fin_score), ptr(st.fin_t),
+                   ptr(st.fin_k), ptr(st.n_fin), ptr(st.done), ptr(st.n_active), sm)
         L.call("vmmt_beam_reorder", fptr(st.h2), fptr(st.h), ptr(st.prev_cur), ptr(st.done), nl, K, B, H, sm)
         L.call("vmmt_beam_reorder", fptr(st.c2), fptr(st.c), ptr(st.prev_cur), ptr(st.done), nl, K, B, H, sm)
         L.call("vmmt_counter_add", ptr(st.step), 1, sm)
@@ -189,8 +204,8 @@ class TranslatorMultimodalVI(object):
         q0, _ = net(context, src_lengths)
         z = q0.mean()                                                     # [B, Z]
         # (2) beam-major tiling (:146-158) into the bucket's static buffers
-        st.ctx.view(S, K, B, H).copy_(context.unsqueeze(1).expand(S, K, B, H))
-        st.len_r.view(K, B).copy_(src_lengths.unsqueeze(0).expand(K, B))
+        st.ctx.copy_(context)
+        st.len_b.copy_(src_lengths)
         h0, c0 = dec._fix_enc_hidden(enc_states[0]), dec._fix_enc_hidden(enc_states[1])
         nl = h0.size(0)
         st.h.view(nl, K, B, H).copy_(h0.unsqueeze(1).expand(nl, K, B, H))
