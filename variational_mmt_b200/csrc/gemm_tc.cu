@@ -35,7 +35,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 4;               // 16 KB
 __host__ __device__ constexpr int b_stage_bytes(int BN) { return BN * BK * 4; }
 __host__ __device__ constexpr int epi_bytes() { return EPI_WARPS * 2 * 4096 + 1024; }   // 2 x 4 KB TMA staging per warp + bias tile
 __host__ __device__ constexpr size_t smem_bytes(int BN, int STAGES) {
-  return 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + b_stage_bytes(BN)) + epi_bytes() + 256;
+  return 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + b_stage_bytes(BN)) + epi_bytes() + 256;   // 256 >= 16*STAGES + 32 (barriers) + 8
 }
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -138,6 +138,7 @@ struct GemmArgs {
   int kb_per_split;      // k-blocks (of BK) per gridDim.z slice
   int tma_store;         // 1: epilogue stores / reduces through the tmC tensor map
   int dbg;
+  int tiles_m, tiles_n; // output tiles (the grid is 1-D over CTAs: persistent tile loop)
   int nkb2;             // k-blocks of the optional second operand pair (C = A B^T + A2 B2^T, both K-major), else 0
   long long* trace;     // debug: per-CTA timeline (8 slots), or null
   // fused generator epilogues (vmmt_internal.h: VmmtGenEpi): 0 none, 1 per-row log-sum-exp partials instead of C,
@@ -367,6 +368,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUten
   __syncwarp();
 }
 
+// Persistent tile loop: CTA `cta` of `ncta` processes tiles cta, cta + ncta, ... (with split-K: exactly one tile per
+// CTA).  Two TMEM accumulators alternate between tiles, so the epilogue warps drain tile i (tcgen05.ld, bias /
+// activation / LSE / top-K, TMA stores) while the MMA warp already contracts tile i+1 and the producer warp runs up to
+// STAGES k-blocks ahead of it -- the smem ring and its phases simply continue across tiles.
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -379,33 +384,32 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(gen + (size_t)STAGES * STAGE);
   const uint32_t bar0 = base + STAGES * STAGE + epi_bytes();
-  // barriers: full[s] at bar0 + 8 s, empty[s] at bar0 + 8 (STAGES + s), tmem_full after them
-  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull = bar0 + 16 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)STAGES * STAGE + epi_bytes() + 16 * STAGES + 8);
+  // barriers: full[s] at bar0 + 8 s, empty[s] after them, then tmem_full[2], tmem_empty[2]
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull0 = bar0 + 16 * STAGES, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)STAGES * STAGE + epi_bytes() + 16 * STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Tile rasterisation: CTAs are scheduled in linear blockIdx order; consecutive CTAs walk DOWN a group of GROUP_M
-  // row-tiles before moving to the next column-tile, so the ~148 co-resident CTAs share GROUP_M A-tiles and ~10 B-tiles
-  // out of L2 instead of one A-tile and 148 B-tiles (the generator's [V,H] weight is larger than L2 at cfg5: without
-  // this every row-tile sweep re-read all of it from HBM -- 39 GB of DRAM traffic for 0.3 GB of operands).
-  int tile_m, tile_n;
-  {
-    constexpr int GROUP_M = 16;
-    const int tiles_n = gridDim.x, tiles_m = gridDim.y;
-    const int lin = blockIdx.x + tiles_n * blockIdx.y;
-    const int grp = lin / (GROUP_M * tiles_n);
-    const int first_m = grp * GROUP_M;
-    const int gm = min(GROUP_M, tiles_m - first_m);
-    const int within = lin - grp * GROUP_M * tiles_n;
-    tile_m = first_m + within % gm;
-    tile_n = within / gm;
-  }
-  const int m0 = tile_m * BM, n0 = tile_n * BN;
   const int nkb_total = (g.K + BK - 1) / BK;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + g.kb_per_split);
-  const int nkb1 = kb1 - kb0;                            // k-blocks of the first operand pair in this CTA
+  const int nkb1 = kb1 - kb0;                            // k-blocks of the first operand pair per tile
   const int nkb = (g.dbg & 2) ? 0 : nkb1 + g.nkb2;       // >= 1 by construction of the grid
+  const int tiles_total = g.tiles_m * g.tiles_n;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+
+  // Tile rasterisation: tiles are numbered so that consecutive ones walk DOWN a group of GROUP_M row-tiles before moving
+  // to the next column-tile: the ~148 co-resident CTAs share GROUP_M A-tiles and ~10 B-tiles out of L2 instead of one
+  // A-tile and 148 B-tiles (the generator's [V,H] weight is larger than L2 at cfg5: without this every row-tile sweep
+  // re-read all of it from HBM -- 39 GB of DRAM traffic for 0.3 GB of operands).
+  auto tile_origin = [&](int lin, int& m0, int& n0) {
+    constexpr int GROUP_M = 16;
+    const int grp = lin / (GROUP_M * g.tiles_n);
+    const int first_m = grp * GROUP_M;
+    const int gm = min(GROUP_M, g.tiles_m - first_m);
+    const int within = lin - grp * GROUP_M * g.tiles_n;
+    m0 = (first_m + within % gm) * BM;
+    n0 = (within / gm) * BN;
+  };
 
   if (threadIdx.x == 0) trace_mark(g.trace, 0);
   if (warp == 0 && lane == 0) {
@@ -422,11 +426,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {   // TMEM allocation (BN fp32 accumulator columns), address written to shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+  if (warp == 2) {   // TMEM allocation (2 x BN fp32 accumulator columns), address written to shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -440,99 +447,124 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // operand of UTMALDG / UTCHMMA into uniform registers with an ELECT + R2UR.BROADCAST loop (~65 cycles per MMA).
   const bool leader = elect_one();
   if (warp == 0) {
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(empty0 + 8 * s, ph ^ 1);
-      const uint32_t fb = full0 + 8 * s;
-      const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
-      const bool second = i >= nkb1;                               // k-blocks of the second operand pair follow the first
-      const int k = second ? (i - nkb1) * BK : (kb0 + i) * BK;
-      const CUtensorMap* pa = second ? &tmA2 : &tmA;
-      const CUtensorMap* pb = second ? &tmB2 : &tmB;
-      if (leader) {
-        mbar_expect_tx(fb, STAGE);
-        if (!A_MN) {
-          tma_load_2d(sa, pa, k, m0, fb);                          // box {32 k, 128 rows}
-        } else {
+    int it = 0;                                          // k-blocks issued so far (ring position across tiles)
+    for (int lin = cta; lin < tiles_total; lin += ncta) {
+      int m0, n0;
+      tile_origin(lin, m0, n0);
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t fb = full0 + 8 * s;
+        const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
+        const bool second = i >= nkb1;                             // k-blocks of the second operand pair follow the first
+        const int k = second ? (i - nkb1) * BK : (kb0 + i) * BK;
+        const CUtensorMap* pa = second ? &tmA2 : &tmA;
+        const CUtensorMap* pb = second ? &tmB2 : &tmB;
+        if (leader) {
+          mbar_expect_tx(fb, STAGE);
+          if (!A_MN) {
+            tma_load_2d(sa, pa, k, m0, fb);                        // box {32 k, 128 rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), pa, m0 + 32 * j, k, fb);   // box {32 m, 32 k}
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, pb, k, n0, fb);                          // box {32 k, BN rows}
-        } else {
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), pa, m0 + 32 * j, k, fb);   // box {32 m, 32 k}
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, pb, k, n0, fb);                        // box {32 k, BN rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), pb, n0 + 32 * j, k, fb);
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), pb, n0 + 32 * j, k, fb);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
                            ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(full0 + 8 * s, ph);
-      if (i == 0 && lane == 0) trace_mark(g.trace, 2);
+    int it = 0, lt = 0;
+    for (int lin = cta; lin < tiles_total; lin += ncta, ++lt) {
+      const int acc = lt & 1;
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+      mbar_wait(tempty0 + 8 * acc, ((lt >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator (2 tiles ago)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        if (lt == 0 && i == 0 && lane == 0) trace_mark(g.trace, 2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
 #pragma unroll
-      for (int j = 0; j < BK / UMMA_K; ++j) {
-        const uint64_t ad = A_MN ? make_desc(sa + j * 1024, BK * 128, 512, 1) : make_desc(sa + j * 32, 16, 1024);
-        const uint64_t bd = B_MN ? make_desc(sb + j * 1024, BK * 128, 512, 1) : make_desc(sb + j * 32, 16, 1024);
-        if (leader) umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        for (int j = 0; j < BK / UMMA_K; ++j) {
+          const uint64_t ad = A_MN ? make_desc(sa + j * 1024, BK * 128, 512, 1) : make_desc(sa + j * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_desc(sb + j * 1024, BK * 128, 512, 1) : make_desc(sb + j * 32, 16, 1024);
+          if (leader) umma_tf32(tacc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        }
+        if (leader) umma_commit(empty0 + 8 * s);          // slot reusable once these MMAs have read it
+        __syncwarp();
       }
-      if (leader) umma_commit(empty0 + 8 * s);          // slot reusable once these MMAs have read it
+      if (leader) umma_commit(tfull0 + 8 * acc);          // accumulator complete
       __syncwarp();
+      if (lt == 0 && lane == 0) trace_mark(g.trace, 3);
     }
-    if (leader) umma_commit(tfull);                      // accumulator complete
-    if (lane == 0) trace_mark(g.trace, 3);
   } else {
     // ---------------- epilogue warps: TMEM lane quarter = warp % 4
     const int q = warp & 3;
     float* sc = epi + (warp - 2) * 2048;            // fallback-path transpose scratch (32 x 33 floats)
-    mbar_wait(tfull, 0);
-    if (threadIdx.x == 64) trace_mark(g.trace, 4);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int mode = (gridDim.z > 1) ? 3 : g.accumulate;        // 0 store, 1 C += v, 2 act(C + v), 3 atomic
-    if ((g.tma_store && mode != 2) || g.epi_mode == 1 || g.epi_mode == 3) {
-      float* bias_s = epi + EPI_WARPS * 2 * 1024;                // [BN] staged once per tile by the 4 warps
-      for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS)
-        bias_s[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t st = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
-      if (g.epi_mode == 1) {
-        epilogue_lse<BN>(g, tmem_base, bias_s, q, lane, m0, n0);
-      } else if (g.epi_mode == 3) {
-        if (g.topk <= 5) epilogue_topk<BN, 5>(g, tmem_base, bias_s, q, lane, m0, n0);
-        else epilogue_topk<BN, VMMT_TOPK_MAX>(g, tmem_base, bias_s, q, lane, m0, n0);
-      } else if (g.epi_mode == 2) {
-        epilogue_tile_tma<BN, VMMT_ACT_NONE, true>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode);
-      } else
-      switch (g.act) {
-        case VMMT_ACT_RELU: epilogue_tile_tma<BN, VMMT_ACT_RELU>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
-        case VMMT_ACT_TANH: epilogue_tile_tma<BN, VMMT_ACT_TANH>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
-        case VMMT_ACT_SOFTPLUS: epilogue_tile_tma<BN, VMMT_ACT_SOFTPLUS>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
-        case VMMT_ACT_SIGMOID: epilogue_tile_tma<BN, VMMT_ACT_SIGMOID>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
-        default: epilogue_tile_tma<BN, VMMT_ACT_NONE>(g, &tmC, tmem_base, st, bias_s, q, lane, m0, n0, mode); break;
+    int lt = 0;
+    for (int lin = cta; lin < tiles_total; lin += ncta, ++lt) {
+      int m0, n0;
+      tile_origin(lin, m0, n0);
+      const int acc = lt & 1;
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+      mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
+      if (lt == 0 && threadIdx.x == 64) trace_mark(g.trace, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if ((g.tma_store && mode != 2) || g.epi_mode == 1 || g.epi_mode == 3) {
+        float* bias_s = epi + EPI_WARPS * 2 * 1024;                // [BN] staged once per tile by the 4 warps
+        if (lt > 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // every warp has finished with the previous tile's bias
+        for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS)
+          bias_s[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t st = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
+        if (g.epi_mode == 1) {
+          epilogue_lse<BN>(g, tacc, bias_s, q, lane, m0, n0);
+        } else if (g.epi_mode == 3) {
+          if (g.topk <= 5) epilogue_topk<BN, 5>(g, tacc, bias_s, q, lane, m0, n0);
+          else epilogue_topk<BN, VMMT_TOPK_MAX>(g, tacc, bias_s, q, lane, m0, n0);
+        } else if (g.epi_mode == 2) {
+          epilogue_tile_tma<BN, VMMT_ACT_NONE, true>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode);
+        } else
+        switch (g.act) {
+          case VMMT_ACT_RELU: epilogue_tile_tma<BN, VMMT_ACT_RELU>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode); break;
+          case VMMT_ACT_TANH: epilogue_tile_tma<BN, VMMT_ACT_TANH>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode); break;
+          case VMMT_ACT_SOFTPLUS: epilogue_tile_tma<BN, VMMT_ACT_SOFTPLUS>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode); break;
+          case VMMT_ACT_SIGMOID: epilogue_tile_tma<BN, VMMT_ACT_SIGMOID>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode); break;
+          default: epilogue_tile_tma<BN, VMMT_ACT_NONE>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode); break;
+        }
+      } else {
+        switch (g.act) {
+          case VMMT_ACT_RELU: epilogue_tile<BN, VMMT_ACT_RELU>(g, tacc, sc, q, lane, m0, n0, mode); break;
+          case VMMT_ACT_TANH: epilogue_tile<BN, VMMT_ACT_TANH>(g, tacc, sc, q, lane, m0, n0, mode); break;
+          case VMMT_ACT_SOFTPLUS: epilogue_tile<BN, VMMT_ACT_SOFTPLUS>(g, tacc, sc, q, lane, m0, n0, mode); break;
+          case VMMT_ACT_SIGMOID: epilogue_tile<BN, VMMT_ACT_SIGMOID>(g, tacc, sc, q, lane, m0, n0, mode); break;
+          default: epilogue_tile<BN, VMMT_ACT_NONE>(g, tacc, sc, q, lane, m0, n0, mode); break;
+        }
       }
-    } else {
-      switch (g.act) {
-        case VMMT_ACT_RELU: epilogue_tile<BN, VMMT_ACT_RELU>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
-        case VMMT_ACT_TANH: epilogue_tile<BN, VMMT_ACT_TANH>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
-        case VMMT_ACT_SOFTPLUS: epilogue_tile<BN, VMMT_ACT_SOFTPLUS>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
-        case VMMT_ACT_SIGMOID: epilogue_tile<BN, VMMT_ACT_SIGMOID>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
-        default: epilogue_tile<BN, VMMT_ACT_NONE>(g, tmem_base, sc, q, lane, m0, n0, mode); break;
-      }
+      // this warp's tcgen05.ld of the accumulator are complete (wait::ld inside the loads): hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+      if (lt == 0 && threadIdx.x == 64) trace_mark(g.trace, 5);
     }
-    if (threadIdx.x == 64) trace_mark(g.trace, 5);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
   }
   if (threadIdx.x == 64) trace_mark(g.trace, 6);
 }
@@ -710,7 +742,7 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
     rc = make_map(&maps.b2, second->B2, second->K2, N, second->ldb2, BN, false);
     if (rc) return rc;
   }
-  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, nkb2, nullptr,
+  GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, tiles_m, ceil_div(N, BN), nkb2, nullptr,
              0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, 0, nullptr, nullptr};
   if (epi) {
     g.epi_mode = epi->mode;
@@ -726,7 +758,11 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
     g.tile_cand = reinterpret_cast<float2*>(epi->tile_cand);
     if (epi->mode == 3 && (epi->topk < 1 || epi->topk > VMMT_TOPK_MAX)) return VMMT_EINVAL;
   }
-  dim3 grid(ceil_div(N, BN), tiles_m, splits);
+  // persistent: one CTA per SM slot when there are more tiles than slots (never with split-K: one tile per CTA)
+  const int tiles = tiles_m * ceil_div(N, BN);
+  const int slots = nsm * (BN == 64 ? 2 : 1);
+  static const int no_persist = getenv("VMMT_GEMM_NO_PERSIST") ? 1 : 0;
+  dim3 grid((splits > 1 || no_persist) ? tiles : min(tiles, slots), 1, splits);
   static long long* trace_buf = nullptr;
   const bool tracing = getenv("VMMT_GEMM_TRACE") != nullptr;
   if (tracing) {
