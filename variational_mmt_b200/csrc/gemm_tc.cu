@@ -662,7 +662,9 @@ bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const floa
   // very thin outputs / contractions stay on the SIMT kernel (a 128-row MMA tile would be almost empty);
   // skinny-M problems (the batch-row MLPs of the latent / image networks) are weight-streaming: they run here
   // with split-K over all SMs and the TMA reduce-add epilogue.
-  if (N < 64 || K < 64 || (int64_t)M * N * K < (int64_t)64 * 64 * 64) return false;
+  // (K >= 16: the K = batch-size weight-gradient products dW += dY^T X of the batch-row MLPs are 1-2 k-blocks deep but
+  //  up to 2048 x 2048 wide -- 40+ us each on the SIMT kernel, a few us here)
+  if (N < 64 || K < 16 || (int64_t)M * N * K < (int64_t)64 * 64 * 64) return false;
   return true;
 }
 

@@ -81,24 +81,41 @@ def _anchor(device):
 # themselves: two of them may accumulate into slices of the same parameter) that forks from the main stream after
 # the tensors they read are complete, and is joined before the gradients are consumed (end of the backward pass /
 # Optim.step).  Under CUDA-graph capture the fork / join become graph edges.
-_side = {"stream": None, "keep": [], "dirty": False, "enabled": True}
+_side = {"streams": [], "keep": [], "dirty": False, "enabled": True, "next": 0, "lanes": 2}
 
 
 def set_side_stream_enabled(flag):
     _side["enabled"] = bool(flag)
 
 
+def _side_stream(lane, device):
+    st = _side["streams"]
+    if not st or st[0].device != device:
+        st[:] = [torch.cuda.Stream(device=device) for _ in range(_side["lanes"])]
+    return st[lane % len(st)]
+
+
 class _OnSide(object):
-    """Issue the enclosed launches on the side stream, ordered after everything already on the current stream."""
+    """Issue the enclosed launches on a side stream, ordered after everything already on the current stream.
+    Successive blocks alternate between ``lanes`` side streams: each block holds the weight / bias gradients of ONE
+    module application (its launches stay ordered among themselves -- dW_hh receives two products), different
+    modules own disjoint parameter memory, so blocks may overlap; what matters is the tail after the last
+    recurrence of the backward pass, where the encoders' weight gradients would otherwise queue up on one stream."""
+
+    def __init__(self, lane=None):
+        self.lane = lane
 
     def __enter__(self):
         self.active = _side["enabled"]
         if not self.active:
             return self
         cur = torch.cuda.current_stream()
-        if _side["stream"] is None or _side["stream"].device != cur.device:
-            _side["stream"] = torch.cuda.Stream(device=cur.device)
-        _side["stream"].wait_stream(cur)
+        if self.lane is None:
+            side = _side_stream(_side["next"], cur.device)
+            _side["next"] += 1
+        else:
+            side = _side_stream(self.lane, cur.device)
+        side.wait_stream(cur)
         if not _side["dirty"]:
             # first side-stream block of this backward pass: join automatically when the pass ends, so that
             # whoever reads .grad afterwards (on the stream that called backward) sees complete gradients
@@ -106,7 +123,7 @@ class _OnSide(object):
                 torch.autograd.Variable._execution_engine.queue_callback(join_side)
             except RuntimeError:
                 pass                                   # not inside a backward pass: the caller joins explicitly
-        self.ctx = torch.cuda.stream(_side["stream"])
+        self.ctx = torch.cuda.stream(side)
         self.ctx.__enter__()
         _side["dirty"] = True
         return self
@@ -117,19 +134,23 @@ class _OnSide(object):
         return False
 
 
-def on_side(*keep):
+def on_side(*keep, lane=None):
     """Context manager; ``keep`` are the tensors the side-stream launches read: they are held until join_side() so
-    that the caching allocator cannot hand their memory to later main-stream work."""
+    that the caching allocator cannot hand their memory to later main-stream work.  ``lane`` pins the block to one
+    of the side streams (default: alternate)."""
     if _side["enabled"]:
         _side["keep"].extend(t for t in keep if t is not None)
-    return _OnSide()
+    return _OnSide(lane)
 
 
 def join_side():
     """The current stream waits for all side-stream work issued so far (call before the gradients are read)."""
-    if _side["dirty"] and _side["stream"] is not None:
-        torch.cuda.current_stream().wait_stream(_side["stream"])
+    if _side["dirty"]:
+        cur = torch.cuda.current_stream()
+        for st in _side["streams"]:
+            cur.wait_stream(st)
     _side["dirty"] = False
+    _side["next"] = 0
     _side["keep"].clear()
 
 
@@ -340,6 +361,7 @@ class LSTMLayerFn(Function):
             ctx.save_for_backward(x, out, gates, cs, h0, c0, rowbias, lengths)
             ctx.weights, ctx.cfg = weights, (ndir, T, N, In, Hd, c0c, c1c)
             ctx.cluster_budget = int(cfg.get("cluster_budget") or 0)
+            ctx.side_lane = cfg.get("side_lane")
         ctx.set_materialize_grads(False)
         return out, hT, cT
 
@@ -388,7 +410,7 @@ class LSTMLayerFn(Function):
             for d in range(ndir):                                          # the term enters every direction
                 colsum_acc(dg[d].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
         # weight / bias gradients (side stream): they only feed the optimiser
-        with on_side(dg, x, out, h0):
+        with on_side(dg, x, out, h0, lane=ctx.side_lane):
             for d in range(ndir):
                 w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
                 dg2 = dg[d].view(T * N, 4 * Hd)
@@ -402,8 +424,16 @@ class LSTMLayerFn(Function):
                     else:
                         a_, b_ = dg[d][:-1], o_d[1:]
                     # rows (t,n) of the shifted views are contiguous blocks with row strides 4Hd / ndir*Hd
-                    gemm(a_.reshape(-1, 4 * Hd), b_.reshape((T - 1) * N, Hd) if ndir == 1 else _rows(b_),
-                         grad_buf(w_hh), 4 * Hd, Hd, (T - 1) * N, a_kmajor=False, b_kmajor=False, accumulate=1)
+                    b2 = b_.reshape((T - 1) * N, Hd) if ndir == 1 else _rows(b_)
+                    if b2.data_ptr() % 16 or b2.stride(0) % 4:
+                        # the reverse direction's half of a bidirectional output starts Hd floats into each row: when
+                        # that is not 16-byte aligned the TMA cannot address it -- stage it in a padded buffer (a 1 MB
+                        # copy) instead of dropping to the SIMT kernel
+                        pad = torch.empty((T - 1) * N, (Hd + 3) // 4 * 4, device=dev, dtype=torch.float32)
+                        pad[:, :Hd].copy_(b2)
+                        b2 = pad[:, :Hd]
+                    gemm(a_.reshape(-1, 4 * Hd), b2, grad_buf(w_hh), 4 * Hd, Hd, (T - 1) * N, a_kmajor=False,
+                         b_kmajor=False, accumulate=1)
                 if w_hh.requires_grad and h0 is not None:                  # first step uses h0
                     t0 = 0 if d == 0 else T - 1
                     gemm(dg[d][t0], h0[d], grad_buf(w_hh), 4 * Hd, Hd, N, a_kmajor=False, b_kmajor=False,
