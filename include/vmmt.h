@@ -118,6 +118,9 @@ int vmmt_masked_mean_fwd(const float* x, const int64_t* lengths, float* out, int
 int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* lengths, float* dx,
                          int accumulate, int T, int B, int H, void* stream);
 int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
+/* stats8 = {nll, n_words, n_correct, kl, img_logprob, img_cos, -, -}: writes loss1[0] = stats8[7] = nll - img_logprob +
+ * kl_weight * kl and stats8[6] = kl_weight * kl (VILoss.py:462-496) in one launch. */
+int vmmt_loss_finalize(float* stats8, float kl_weight, float* loss1, void* stream);
 /* out[N] (+= column sums of a[M,N]); out2 (optional) receives the same sums (nn.LSTM's b_ih / b_hh pair). */
 int vmmt_colsum_acc(const float* a, int64_t lda, int M, int N, float* out, float* out2, void* stream);
 int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);

@@ -159,10 +159,7 @@ class NMTVIModel1LossCompute(nn.Module):
             None if pz_location is None else pz_location.squeeze(0),
             None if pz_scale is None else pz_scale.squeeze(0),
             p_global_image_features_location.squeeze(0), ground_truth_global_image_features.squeeze(0), cfg)
-        with torch.no_grad():
-            vec = stats.clone()
-            vec[6] = vec[3] * kw                       # td_kl_after
-            vec[7] = loss[0]                           # elbo
+        vec = stats                                    # [6] = td_kl_after, [7] = elbo filled by vmmt_loss_finalize
         loss_data = {"_vec": vec, "two_step_image_prediction": False, "image_loss_type": self.image_loss_type,
                      "td_kl_multiplier": self.kl_annealing_current}
         batch_stats = VIStatistics(self.multimodal_model_type, loss_data)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "vmmt_masked_mean_fwd": (I, [P, P, P, L, I, I, I, P]),
     "vmmt_masked_mean_bwd": (I, [P, L, P, P, I, I, I, I, P]),
     "vmmt_act_bwd": (I, [P, P, P, L, I, P]),
+    "vmmt_loss_finalize": (I, [P, F, P, P]),
     "vmmt_colsum_acc": (I, [P, L, I, I, P, P, P]),
     "vmmt_axpy": (I, [P, P, F, L, P]),
     "vmmt_counter_add": (I, [P, U64, P]),

@@ -1,6 +1,7 @@
 // Memory-bound kernels of the VI-model-1 step: embedding gather / scatter, masked mean,
 // activation derivatives, bias-gradient column sums, Philox dropout, the latent block
 // (sample + analytic KL) and the image-feature head's gate and loss.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "vmmt_internal.h"
 
@@ -50,20 +51,30 @@ __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, int64_t d
 }
 
 // ---------------------------------------------------------------- activation derivatives (from outputs)
+__device__ __forceinline__ float act_grad(float g, float v, int act) {
+  switch (act) {
+    case VMMT_ACT_RELU: return v > 0.f ? g : 0.f;
+    case VMMT_ACT_TANH: return g * (1.f - v * v);
+    case VMMT_ACT_SOFTPLUS: return g * (1.f - expf(-v));     // sigmoid(pre) = 1 - exp(-softplus)
+    case VMMT_ACT_SIGMOID: return g * v * (1.f - v);
+    default: return g;
+  }
+}
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                float* __restrict__ dx, int64_t n, int act) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = y[i], g = dy[i];
-  float d;
-  switch (act) {
-    case VMMT_ACT_RELU: d = v > 0.f ? g : 0.f; break;
-    case VMMT_ACT_TANH: d = g * (1.f - v * v); break;
-    case VMMT_ACT_SOFTPLUS: d = g * (1.f - expf(-v)); break;     // sigmoid(pre) = 1 - exp(-softplus)
-    case VMMT_ACT_SIGMOID: d = g * v * (1.f - v); break;
-    default: d = g;
-  }
-  dx[i] = d;
+  dx[i] = act_grad(dy[i], y[i], act);
+}
+// 16-byte aligned buffers: four elements per thread
+__global__ void __launch_bounds__(256)
+act_bwd4_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ dx,
+                int64_t n4, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 g = dy[i], v = y[i];
+  dx[i] = make_float4(act_grad(g.x, v.x, act), act_grad(g.y, v.y, act), act_grad(g.z, v.z, act),
+                      act_grad(g.w, v.w, act));
 }
 
 // column sums of a row-major [M,N] matrix (bias gradients), accumulated into out[N]
@@ -119,18 +130,35 @@ __global__ void sample_kernel(const float* __restrict__ mu, const float* __restr
 
 // KL[N(mu_q,sd_q) || N(mu_p,sd_p)] summed over Z, mean over B (VILoss.py:439-460).
 // One block; out[0] = KL.  mu_p / sd_p may be null (standard normal prior, Models.py:936-939).
-__global__ void kl_fwd_kernel(const float* __restrict__ mq, const float* __restrict__ sq,
-                              const float* __restrict__ mp, const float* __restrict__ sp,
-                              float* __restrict__ out, int B, int Z) {
+// One thread-block cluster of KL_CTAS CTAs: each reduces a contiguous slice, the block sums meet in CTA 0's shared
+// memory through DSMEM and are added in rank order (deterministic; no global scratch, no atomics).
+constexpr int KL_CTAS = 8;
+__global__ void __cluster_dims__(KL_CTAS, 1, 1) __launch_bounds__(512)
+kl_fwd_kernel(const float* __restrict__ mq, const float* __restrict__ sq,
+              const float* __restrict__ mp, const float* __restrict__ sp,
+              float* __restrict__ out, int B, int Z) {
   __shared__ float red[32];
+  __shared__ float part[KL_CTAS];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int n = B * Z;
+  const int per = (n + KL_CTAS - 1) / KL_CTAS;
+  const int lo = rank * per, hi = min(n, lo + per);
   float s = 0.f;
-  for (int i = threadIdx.x; i < B * Z; i += blockDim.x) {
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float m2 = mp ? mp[i] : 0.f, s2 = sp ? sp[i] : 1.f;
     const float d = mq[i] - m2, v1 = sq[i] * sq[i], v2 = s2 * s2;
     s += 0.5f / v2 * (d * d + v1 - v2) + logf(s2) - logf(sq[i]);
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) out[0] = s / (float)B;
+  if (threadIdx.x == 0) *cluster.map_shared_rank(&part[rank], 0) = s;
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    float t = 0.f;
+    for (int r = 0; r < KL_CTAS; ++r) t += part[r];
+    out[0] = t / (float)B;
+  }
 }
 // gradients scaled by *gscale (device scalar) * kl_weight / B
 __global__ void kl_bwd_kernel(const float* __restrict__ mq, const float* __restrict__ sq,
@@ -276,6 +304,11 @@ extern "C" int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const in
 extern "C" int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act,
                             void* stream) {
   if (n <= 0) return VMMT_OK;
+  if ((n & 3) == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) == 0) {
+    act_bwd4_kernel<<<ceil_div(n / 4, 256), 256, 0, ST(stream)>>>((const float4*)dy, (const float4*)y, (float4*)dx,
+                                                                 n / 4, act);
+    return vmmt_check_launch("act_bwd4");
+  }
   act_bwd_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(dy, y, dx, n, act);
   return vmmt_check_launch("act_bwd");
 }
@@ -293,6 +326,19 @@ extern "C" int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void*
   return vmmt_check_launch("axpy");
 }
 __global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { *ctr += inc; }
+
+// stats = {nll, n_words, n_correct, kl, img_logprob, img_cos, kl_after, elbo}: objective and the two derived entries
+// in one launch (onmt/VILoss.py:462-496: loss = nll - img_logprob + kl_weight * kl)
+__global__ void loss_finalize_kernel(float* __restrict__ stats, float kl_weight, float* __restrict__ loss) {
+  const float l = stats[0] - stats[4] + kl_weight * stats[3];
+  stats[6] = stats[3] * kl_weight;
+  stats[7] = l;
+  loss[0] = l;
+}
+extern "C" int vmmt_loss_finalize(float* stats8, float kl_weight, float* loss1, void* stream) {
+  loss_finalize_kernel<<<1, 1, 0, ST(stream)>>>(stats8, kl_weight, loss1);
+  return vmmt_check_launch("loss_finalize");
+}
 
 extern "C" int vmmt_counter_add(uint64_t* ctr, uint64_t inc, void* stream) {
   counter_add_kernel<<<1, 1, 0, ST(stream)>>>(ctr, inc);
@@ -313,7 +359,7 @@ extern "C" int vmmt_normal_sample(const float* mu, const float* sd, const float*
 }
 extern "C" int vmmt_kl_fwd(const float* mu_q, const float* sd_q, const float* mu_p,
                            const float* sd_p, float* out, int B, int Z, void* stream) {
-  kl_fwd_kernel<<<1, 1024, 0, ST(stream)>>>(mu_q, sd_q, mu_p, sd_p, out, B, Z);
+  kl_fwd_kernel<<<KL_CTAS, 512, 0, ST(stream)>>>(mu_q, sd_q, mu_p, sd_p, out, B, Z);
   return vmmt_check_launch("kl_fwd");
 }
 extern "C" int vmmt_kl_bwd(const float* mu_q, const float* sd_q, const float* mu_p,

@@ -577,6 +577,9 @@ def gate(z, weight, bias):
     return GateFn.apply(_anchor(z.device), z, _P(weight), _P(bias))
 
 
+_loss_stream = None
+
+
 class VILossFn(Function):
     """NLL + image log-prob + KL in one node (onmt/VILoss.py:217-513).
 
@@ -597,19 +600,28 @@ class VILossFn(Function):
         lse = torch.empty(M, device=dev, dtype=torch.float32)
         wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
-        L.call("vmmt_generator_nll_fwd", fptr(out2d), fptr(gen_w), fptr(gen_b), ptr(target), cfg["pad_idx"],
-               M, H, V, fptr(lse), fptr(stats[0:3]), fptr(ws), wsb, stream())
         mu_q, sd_q = mu_q.contiguous(), sd_q.contiguous()
         B, Z = mu_q.shape
         if mu_p is not None:
             mu_p, sd_p = mu_p.contiguous(), sd_p.contiguous()
-        L.call("vmmt_kl_fwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(stats[3:4]), B, Z, stream())
         img_loc, img_v = img_loc.contiguous(), img_v.contiguous()
         D = img_loc.shape[1]
         rowstats = torch.empty(B, 4, device=dev, dtype=torch.float32)
-        L.call("vmmt_image_loss_fwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(stats[4:6]), B, D, stream())
+        # KL and image terms do not depend on the generator: they run on their own stream beside its GEMM
+        cur = torch.cuda.current_stream(dev)
+        global _loss_stream
+        if _loss_stream is None or _loss_stream.device != dev:
+            _loss_stream = torch.cuda.Stream(device=dev)
+        _loss_stream.wait_stream(cur)
+        with torch.cuda.stream(_loss_stream):
+            L.call("vmmt_kl_fwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(stats[3:4]), B, Z, stream())
+            L.call("vmmt_image_loss_fwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(stats[4:6]), B, D, stream())
+        L.call("vmmt_generator_nll_fwd", fptr(out2d), fptr(gen_w), fptr(gen_b), ptr(target), cfg["pad_idx"],
+               M, H, V, fptr(lse), fptr(stats[0:3]), fptr(ws), wsb, stream())
+        cur.wait_stream(_loss_stream)
         kw = float(cfg["kl_weight"])
-        loss = (stats[0] - stats[4] + kw * stats[3]).reshape(1)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        L.call("vmmt_loss_finalize", fptr(stats), kw, fptr(loss), stream())     # also stats[6] = kw * kl, stats[7] = loss
         ctx.save_for_backward(out2d, target, lse, mu_q, sd_q, mu_p, sd_p, img_loc, img_v, rowstats)
         ctx.gen_w, ctx.gen_b, ctx.cfg = gen_w, gen_b, cfg
         ctx.mark_non_differentiable(stats)
