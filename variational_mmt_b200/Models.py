@@ -152,6 +152,10 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
                 padding_token=None):
         orig_tgt = tgt
         tgt = tgt[:-1]
+        dec_gx = None
+        if self.training and dec_state is None and hasattr(self.decoder, "input_projection"):
+            with ops.branch(lane=2):                       # decoder input projection: independent of everything below
+                dec_gx = self.decoder.input_projection(tgt)
         if self.conditional:
             # target encoder over the transposed ids: recurrence along the batch axis (hazard H1).  It does not depend
             # on the source encoder: the two stacks run side by side on two streams, each on its share of the SMs
@@ -177,8 +181,12 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         with ops.branch():                                                       # p(v|z) beside the decoder
             p_v, _ = self.inf_net_image(z0_sample, context, lengths)
         enc_state = self.decoder.init_decoder_state(src, context, enc_hidden)
+        extra = {}
+        if dec_gx is not None:
+            ops.join_branch(dec_gx, lane=2)
+            extra["input_projection"] = dec_gx
         out, dec_state, attns = self.decoder(tgt, context, enc_state if dec_state is None else dec_state,
-                                             lengths, image_features=None, z_sample=z0_sample)
+                                             lengths, image_features=None, z_sample=z0_sample, **extra)
         ops.join_branch(p_v.mean(), *([] if getattr(pz0, "is_standard", False) else pz0.params()))
         attns["p_global_image_features"] = [p_v]
         attns["ground_truth_global_image_features"] = [img_feats]

@@ -19,14 +19,26 @@ class StdRNNVIModel1Decoder(RNNVIDecoderBase):
             "Must provide the following parameters in kwargs: ['z_sample', 'image_features']"
         z_sample = kwargs["z_sample"]
         assert kwargs["image_features"] is None, "Model 'vi-model1' does not use image features in the decoder!"
-        emb = self.embeddings(input)                                           # [T,B,E]
         E = self.embeddings.embedding_size
         w0 = self.rnn.weight_ih_l0
         zb = ops.linear(z_sample.detach(), w0, cols=(E, E + self.latent_dim))     # [B,4H]
-        rnn_output, hidden = self.rnn(emb, state.hidden, in_bias=zb, in_cols=(0, E))
+        gx0 = kwargs.get("input_projection")
+        if gx0 is None:
+            emb = self.embeddings(input)                                       # [T,B,E]
+            rnn_output, hidden = self.rnn(emb, state.hidden, in_bias=zb, in_cols=(0, E))
+        else:                                              # emb(tgt) W_ih[:, :E]^T was computed ahead of the encoders
+            rnn_output, hidden = self.rnn(gx0, state.hidden, in_bias=zb, in_cols=(0, E), gx_given=True)
         attn_h, align = self.attn.forward_time_major(rnn_output, context, context_lengths)
         outputs = ops.dropout(attn_h, self.dropout_p, self.training)
         return hidden, outputs, {"std": align}, None
+
+    def input_projection(self, input):
+        """emb(tgt) W_ih[:, :E]^T [T,B,4H]: the part of the first layer's gate pre-activations that depends on neither
+        the encoders nor z (VI_Model1.py:94-106 concatenates [emb ; z] before the LSTM).  NMTVIModel.forward issues it
+        on a branch stream before the encoders, so it (and, in the backward pass, dW_ih / the embedding gradient) is
+        off the step's critical path."""
+        E = self.embeddings.embedding_size
+        return ops.linear(self.embeddings(input), self.rnn.weight_ih_l0, cols=(0, E))
 
     def _build_rnn(self, rnn_type, input_size, hidden_size, num_layers, dropout):
         return LSTM(input_size + self.latent_dim, hidden_size, num_layers=num_layers, dropout=dropout)

@@ -39,9 +39,10 @@ class LSTM(nn.Module):
             out += [getattr(self, f"{n}_l{l}{sfx}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
         return out
 
-    def forward(self, input, hx=None, lengths=None, in_bias=None, in_cols=None):
+    def forward(self, input, hx=None, lengths=None, in_bias=None, in_cols=None, gx_given=False):
         """input [T,N,In]; hx = (h0, c0) each [layers*ndir, N, H] or None ->
-        output [T,N,ndir*H], (h_n, c_n) each [layers*ndir, N, H]"""
+        output [T,N,ndir*H], (h_n, c_n) each [layers*ndir, N, H].  ``gx_given``: ``input`` already is layer 0's
+        input projection x W_ih[:, in_cols]^T [T,N,4H] (computed ahead of time on another stream)."""
         ndir = 2 if self.bidirectional else 1
         save = torch.is_grad_enabled()
         x = input
@@ -51,7 +52,7 @@ class LSTM(nn.Module):
                 x = ops.dropout(x, self.dropout, self.training)
             h0 = hx[0][l * ndir:(l + 1) * ndir] if hx is not None else None
             c0 = hx[1][l * ndir:(l + 1) * ndir] if hx is not None else None
-            cfg = {"save": save, "in_cols": in_cols if l == 0 else None,
+            cfg = {"save": save, "in_cols": in_cols if l == 0 else None, "gx_given": gx_given and l == 0,
                    "cluster_budget": self.cluster_budget if self.training else None,
                    # weight gradients of a bidirectional stack (the target encoder) and of a unidirectional one (source
                    # encoder / decoder) go to different side streams: the two encoders' backward passes run

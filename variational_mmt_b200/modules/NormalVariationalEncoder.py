@@ -75,7 +75,13 @@ class GlobalFullInferenceNetwork(GlobalInferenceNetwork):
         hx = self.encode_seq(x, x_lengths)
         hy = self.encode_seq(y, y_lengths)
         h = torch.cat([hx, hy, v], -1)
-        return Normal(self.location(h), self.scale(h)), h
+        # q(z|x,y,v) sits on the step's critical path (target encoder -> here -> decoder): its two independent MLPs run
+        # side by side (the scale MLP on branch lane 1; autograd replays the same split in the backward pass)
+        with ops.branch(lane=1):
+            scale = self.scale(h)
+        loc = self.location(h)
+        ops.join_branch(scale, lane=1)
+        return Normal(loc, scale), h
 
 
 class ImageGlobalInferenceNetwork(GlobalInferenceNetwork):

@@ -156,23 +156,29 @@ def join_side():
 
 # ---- branch stream: independent sub-graphs of the forward pass (and, through autograd's per-node streams, of the
 # backward pass) run beside the main chain: prior network and image-feature head beside the decoder ----------------
-_branch = {"stream": None, "enabled": True}
+_branch = {"streams": {}, "enabled": True}
 
 
 class branch(object):
-    """``with ops.branch(): ...`` issues the enclosed module calls on the branch stream, ordered after everything
+    """``with ops.branch(): ...`` issues the enclosed module calls on a branch stream, ordered after everything
     already on the current stream.  Autograd nodes created inside remember that stream, so their backward runs
-    there too.  ``ops.join_branch(*tensors)`` makes the current stream wait and hands the tensors over."""
+    there too.  ``ops.join_branch(*tensors)`` makes the current stream wait and hands the tensors over.
+    ``lane`` selects one of several branch streams (0: encoder / prior / image head beside the main chain,
+    1: the scale MLP of the posterior beside its location MLP); blocks may nest across lanes."""
+
+    def __init__(self, lane=0):
+        self.lane = lane
 
     def __enter__(self):
         self.active = _branch["enabled"] and torch.cuda.is_available()
         if not self.active:
             return self
         cur = torch.cuda.current_stream()
-        if _branch["stream"] is None or _branch["stream"].device != cur.device:
-            _branch["stream"] = torch.cuda.Stream(device=cur.device)
-        _branch["stream"].wait_stream(cur)
-        self.ctx = torch.cuda.stream(_branch["stream"])
+        st = _branch["streams"].get(self.lane)
+        if st is None or st.device != cur.device:
+            st = _branch["streams"][self.lane] = torch.cuda.Stream(device=cur.device)
+        st.wait_stream(cur)
+        self.ctx = torch.cuda.stream(st)
         self.ctx.__enter__()
         return self
 
@@ -182,11 +188,12 @@ class branch(object):
         return False
 
 
-def join_branch(*tensors):
-    if _branch["stream"] is None or not _branch["enabled"]:
+def join_branch(*tensors, lane=0):
+    st = _branch["streams"].get(lane)
+    if st is None or not _branch["enabled"]:
         return
     cur = torch.cuda.current_stream()
-    cur.wait_stream(_branch["stream"])
+    cur.wait_stream(st)
     for t in tensors:
         if t is not None and t.is_cuda:
             t.record_stream(cur)
@@ -324,9 +331,14 @@ class LSTMLayerFn(Function):
         dev = x.device
         x = x.contiguous()
         save = cfg.get("save", True)
+        gx_given = bool(cfg.get("gx_given"))     # x IS the input projection x W_ih^T (computed earlier, off the critical path)
         c0c, c1c = cfg.get("in_cols") or (0, weights[0].shape[1])
-        assert c1c - c0c == In
-        gx = torch.empty(ndir, T, N, 4 * Hd, device=dev, dtype=torch.float32)
+        if gx_given:
+            assert ndir == 1 and In == 4 * Hd, "precomputed gate pre-activations: one direction, [T,N,4H]"
+            gx = x.view(1, T, N, 4 * Hd)
+        else:
+            assert c1c - c0c == In
+            gx = torch.empty(ndir, T, N, 4 * Hd, device=dev, dtype=torch.float32)
         out = torch.empty(T, N, ndir * Hd, device=dev, dtype=torch.float32)
         hT = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32)
         cT = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32)
@@ -340,7 +352,8 @@ class LSTMLayerFn(Function):
         x2 = x.view(T * N, In)
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
-            gemm(x2, w_ih[:, c0c:c1c], gx[d].view(T * N, 4 * Hd), T * N, 4 * Hd, In)
+            if not gx_given:
+                gemm(x2, w_ih[:, c0c:c1c], gx[d].view(T * N, 4 * Hd), T * N, 4 * Hd, In)
             D = dirs[d]
             D.gx, D.w_hh, D.b_ih, D.b_hh = fptr(gx[d]), fptr(w_hh), fptr(b_ih), fptr(b_hh)
             D.rowbias = fptr(rowbias)
@@ -358,8 +371,9 @@ class LSTMLayerFn(Function):
         L.call("vmmt_lstm_seq_fwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
         L.lib.vmmt_lstm_set_cluster_budget(0)
         if save:
-            ctx.save_for_backward(x, out, gates, cs, h0, c0, rowbias, lengths)
+            ctx.save_for_backward(None if gx_given else x, out, gates, cs, h0, c0, rowbias, lengths)
             ctx.weights, ctx.cfg = weights, (ndir, T, N, In, Hd, c0c, c1c)
+            ctx.gx_given = gx_given
             ctx.cluster_budget = int(cfg.get("cluster_budget") or 0)
             ctx.side_lane = cfg.get("side_lane")
         ctx.set_materialize_grads(False)
@@ -370,7 +384,8 @@ class LSTMLayerFn(Function):
         x, out, gates, cs, h0, c0, rowbias, lengths = ctx.saved_tensors
         weights = ctx.weights
         ndir, T, N, In, Hd, c0c, c1c = ctx.cfg
-        dev = x.device
+        gx_given = ctx.gx_given
+        dev = out.device
         dout = dout.contiguous() if dout is not None else None
         dhT = dhT.contiguous() if dhT is not None else None
         dcT = dcT.contiguous() if dcT is not None else None
@@ -396,8 +411,9 @@ class LSTMLayerFn(Function):
         L.lib.vmmt_lstm_set_cluster_budget(ctx.cluster_budget)
         L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
         L.lib.vmmt_lstm_set_cluster_budget(0)
-        x2 = x.view(T * N, In)
-        dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        x2 = x.view(T * N, In) if not gx_given else None
+        dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) \
+            if (ctx.needs_input_grad[1] and not gx_given) else None
         drow = None
         # critical path (main stream): what the layers below / the callers wait for
         for d in range(ndir):
@@ -414,7 +430,7 @@ class LSTMLayerFn(Function):
             for d in range(ndir):
                 w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
                 dg2 = dg[d].view(T * N, 4 * Hd)
-                if w_ih.requires_grad:                                     # dW_ih += dG^T x
+                if w_ih.requires_grad and not gx_given:                    # dW_ih += dG^T x
                     gemm(dg2, x2, grad_buf(w_ih)[:, c0c:c1c], 4 * Hd, In, T * N, a_kmajor=False,
                          b_kmajor=False, accumulate=1)
                 if w_hh.requires_grad and T > 1:                           # dW_hh += dG[t]^T h[t -/+ 1]
@@ -444,6 +460,8 @@ class LSTMLayerFn(Function):
                     colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih if b_ih.requires_grad else b_hh))
         if dx is not None:
             dx = dx.view(T, N, In)
+        if gx_given and ctx.needs_input_grad[1]:
+            dx = dg[0]                 # d(gate pre-activations): the node that produced gx takes dW_ih / dx from it
         return None, dx, dh0, dc0, drow, None, None, None
 
 
