@@ -153,9 +153,6 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         orig_tgt = tgt
         tgt = tgt[:-1]
         dec_gx = None
-        if self.training and dec_state is None and hasattr(self.decoder, "input_projection"):
-            with ops.branch(lane=2):                       # decoder input projection: independent of everything below
-                dec_gx = self.decoder.input_projection(tgt)
         if self.conditional:
             # target encoder over the transposed ids: recurrence along the batch axis (hazard H1).  It does not depend
             # on the source encoder: the two stacks run side by side on two streams, each on its share of the SMs
@@ -164,8 +161,16 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
                 tgt_context = tgt_context.transpose(0, 1)
         enc_hidden, context = self.encoder(src, lengths)
         if self.conditional:
-            assert isinstance(self.inf_net_global, GlobalFullInferenceNetwork)
             ops.join_branch(tgt_context)
+        if self.training and dec_state is None and hasattr(self.decoder, "input_projection"):
+            # decoder input projection emb(tgt) W_ih[:, :E]^T: needs neither the encoders nor z.  It is issued HERE, beside
+            # the latent networks (batch-row MLPs that leave most SMs idle), and not beside the encoder recurrences: a
+            # GEMM that fills the SMs keeps the recurrences' thread-block clusters from being placed (measured: the
+            # target encoder's first layer went from 80 to 183 us with the projection issued at the top of the step)
+            with ops.branch(lane=2):
+                dec_gx = self.decoder.input_projection(tgt)
+        if self.conditional:
+            assert isinstance(self.inf_net_global, GlobalFullInferenceNetwork)
             with ops.branch():                                                   # p(z|x): only the KL needs it in training
                 pz0, _ = self.gen_net_global(context, lengths)
             if not self.training:

@@ -189,6 +189,10 @@ class NMTVIModel1LossCompute(nn.Module):
         state["output"] = state["output"][:shard_size]
         state["target"] = state["target"][:shard_size]
         loss, stats = self._compute_loss(batch, **state)
+        hook = getattr(self, "before_backward", None)      # GraphedTrainStep: join the gradient memset issued beside the loss
+        if hook is not None:
+            hook()
+            self.before_backward = None
         loss.div(normalization).backward()
         ops.join_side()                 # weight-gradient GEMMs issued on the side stream are complete from here on
         batch_stats.update(stats)

@@ -51,15 +51,17 @@ class GraphedTrainStep(object):
         ops.rng_base(self.device)
 
     def _run(self, src, sl, tgt, tl, img, normalization):
-        # the 171 MB gradient memset runs beside the forward pass (nothing reads or writes a gradient before the loss)
+        out, attns, _ = self.model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
+        # the 171 MB gradient memset runs beside the generator / loss forward (nothing touches a gradient before the
+        # backward pass).  Not earlier: its thousands of short blocks keep the encoder recurrences' thread-block
+        # clusters from being placed (measured +30 us on the source encoder's first layer)
         cur = torch.cuda.current_stream(self.device)
         if self._zero_stream is None:
             self._zero_stream = torch.cuda.Stream(device=self.device)
         self._zero_stream.wait_stream(cur)
         with torch.cuda.stream(self._zero_stream):
             self.model.zero_grad()
-        out, attns, _ = self.model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
-        cur.wait_stream(self._zero_stream)
+        self.loss.before_backward = lambda: cur.wait_stream(self._zero_stream)
         st = self.loss.sharded_compute_loss(_Batch(tgt, tgt.size(1)), out, attns, 0, tgt.size(0),
                                             self.shard_size, normalization)
         return st._vec
