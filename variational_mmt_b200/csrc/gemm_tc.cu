@@ -34,8 +34,15 @@ constexpr int A_STAGE_BYTES = BM * BK * 4;               // 16 KB
 
 __host__ __device__ constexpr int b_stage_bytes(int BN) { return BN * BK * 4; }
 __host__ __device__ constexpr int epi_bytes() { return EPI_WARPS * 2 * 4096 + 1024; }   // 2 x 4 KB TMA staging per warp + bias tile
+// Every GEMM CTA asks for at least EXCLUSIVE_SMEM bytes of dynamic shared memory, i.e. for an SM of its own as far as
+// other tensor-memory users go: the LSTM recurrence kernels (lstm_tc.cu) allocate all 512 TMEM columns for the whole
+// sequence, so a GEMM CTA placed beside one would sit in tcgen05.alloc until the recurrence ends (and a recurrence
+// CTA placed beside a GEMM CTA stalls its whole cluster: measured 148 -> 222 us on the last encoder layer when the
+// register footprints happened to allow co-residency).  21 KB (smallest recurrence CTA) + 208 KB > 227 KB.
+constexpr size_t EXCLUSIVE_SMEM = 208 * 1024;
 __host__ __device__ constexpr size_t smem_bytes(int BN, int STAGES) {
-  return 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + b_stage_bytes(BN)) + epi_bytes() + 256;   // 256 >= 16*STAGES + 32 (barriers) + 8
+  const size_t need = 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + b_stage_bytes(BN)) + epi_bytes() + 256;   // 256 >= 16*STAGES + 32 (barriers) + 8
+  return need > EXCLUSIVE_SMEM ? need : EXCLUSIVE_SMEM;
 }
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -372,7 +379,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUten
 // CTA).  Two TMEM accumulators alternate between tiles, so the epilogue warps drain tile i (tcgen05.ld, bias /
 // activation / LSE / top-K, TMA stores) while the MMA warp already contracts tile i+1 and the producer warp runs up to
 // STAGES k-blocks ahead of it -- the smem ring and its phases simply continue across tiles.
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// GEN = true instantiates the generator epilogues (LSE / dlogits / top-K); they roughly double the register count, so the
+// plain GEMMs get their own instantiation (96 instead of 180 registers per thread: two 64-wide CTAs per SM, and room
+// for a recurrence CTA beside a weight-gradient CTA on the same SM).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool GEN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
@@ -523,20 +533,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
       if (lt == 0 && threadIdx.x == 64) trace_mark(g.trace, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if ((g.tma_store && mode != 2) || g.epi_mode == 1 || g.epi_mode == 3) {
+      if ((g.tma_store && mode != 2) || (GEN && (g.epi_mode == 1 || g.epi_mode == 3))) {
         float* bias_s = epi + EPI_WARPS * 2 * 1024;                // [BN] staged once per tile by the 4 warps
         if (lt > 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // every warp has finished with the previous tile's bias
         for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS)
           bias_s[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const uint32_t st = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
-        if (g.epi_mode == 1) {
-          epilogue_lse<BN>(g, tacc, bias_s, q, lane, m0, n0);
-        } else if (g.epi_mode == 3) {
-          if (g.topk <= 5) epilogue_topk<BN, 5>(g, tacc, bias_s, q, lane, m0, n0);
-          else epilogue_topk<BN, VMMT_TOPK_MAX>(g, tacc, bias_s, q, lane, m0, n0);
-        } else if (g.epi_mode == 2) {
-          epilogue_tile_tma<BN, VMMT_ACT_NONE, true>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode);
+        if (GEN && g.epi_mode == 1) {
+          if constexpr (GEN) epilogue_lse<BN>(g, tacc, bias_s, q, lane, m0, n0);
+        } else if (GEN && g.epi_mode == 3) {
+          if constexpr (GEN) {
+            if (g.topk <= 5) epilogue_topk<BN, 5>(g, tacc, bias_s, q, lane, m0, n0);
+            else epilogue_topk<BN, VMMT_TOPK_MAX>(g, tacc, bias_s, q, lane, m0, n0);
+          }
+        } else if (GEN && g.epi_mode == 2) {
+          if constexpr (GEN) epilogue_tile_tma<BN, VMMT_ACT_NONE, true>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode);
         } else
         switch (g.act) {
           case VMMT_ACT_RELU: epilogue_tile_tma<BN, VMMT_ACT_RELU>(g, &tmC, tacc, st, bias_s, q, lane, m0, n0, mode); break;
@@ -630,9 +642,9 @@ int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int6
 
 struct Maps { CUtensorMap a, b, c, a2, b2; };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool GEN = false>
 int launch(const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
-  auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN, GEN>;
   static bool attr_done = false;        // per instantiation
   constexpr size_t smem = smem_bytes(BN, STAGES);
   if (!attr_done) {
@@ -645,6 +657,10 @@ int launch(const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
 
 template <int BN, int STAGES>
 int launch_major(bool a_mn, bool b_mn, const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
+  if (g.epi_mode != 0) {                 // generator epilogues: x [M,H] and W [V,H] are both K-major
+    if (a_mn || b_mn || BN != 128) return VMMT_EINVAL;
+    return launch<128, STAGES, false, false, true>(m, g, grid, s);
+  }
   if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(m, g, grid, s);
   if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(m, g, grid, s);
   if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(m, g, grid, s);
@@ -696,7 +712,7 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   double best = 1e30;
   for (int bn = (epi ? 128 : 64); bn <= 128; bn *= 2) {
     const int tiles = tiles_m * ceil_div(N, bn);
-    const int slots = nsm * (bn == 64 ? 2 : 1);
+    const int slots = nsm;
     const int max_split = can_split ? min(32, max(1, nkb / 4)) : 1;
     for (int sp = 1; sp <= max_split; ++sp) {
       const int kb = ceil_div(nkb, sp);
@@ -762,7 +778,7 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   }
   // persistent: one CTA per SM slot when there are more tiles than slots (never with split-K: one tile per CTA)
   const int tiles = tiles_m * ceil_div(N, BN);
-  const int slots = nsm * (BN == 64 ? 2 : 1);
+  const int slots = nsm;                       // one CTA per SM (EXCLUSIVE_SMEM)
   static const int no_persist = getenv("VMMT_GEMM_NO_PERSIST") ? 1 : 0;
   dim3 grid((splits > 1 || no_persist) ? tiles : min(tiles, slots), 1, splits);
   static long long* trace_buf = nullptr;
