@@ -46,6 +46,7 @@ class GraphedTrainStep(object):
         self._graphs = {}
         self._pool = None
         self._zero_stream = None
+        self._capture_stream = None
         self.kernels_per_replay = 0          # libvmmt kernels inside the most recently captured graph
         self.device = next(model.parameters()).device
         ops.rng_base(self.device)
@@ -83,7 +84,11 @@ class GraphedTrainStep(object):
         torch.cuda.current_stream(self.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         l0 = _lib.lib.vmmt_launch_count()
-        with torch.cuda.graph(g, pool=self._pool):
+        # captured on a HIGH-priority stream (as are the branch / loss streams): kernel-node priorities are recorded, so
+        # the critical chain's CTAs are placed before those of the weight-gradient lanes (default = lowest priority)
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        with torch.cuda.graph(g, pool=self._pool, stream=self._capture_stream):
             ops.begin_step()
             vec = self._run(*static, normalization)
             ops.advance_rng()

@@ -176,7 +176,7 @@ class branch(object):
         cur = torch.cuda.current_stream()
         st = _branch["streams"].get(self.lane)
         if st is None or st.device != cur.device:
-            st = _branch["streams"][self.lane] = torch.cuda.Stream(device=cur.device)
+            st = _branch["streams"][self.lane] = torch.cuda.Stream(device=cur.device, priority=-1)
         st.wait_stream(cur)
         self.ctx = torch.cuda.stream(st)
         self.ctx.__enter__()
@@ -629,7 +629,7 @@ class VILossFn(Function):
         cur = torch.cuda.current_stream(dev)
         global _loss_stream
         if _loss_stream is None or _loss_stream.device != dev:
-            _loss_stream = torch.cuda.Stream(device=dev)
+            _loss_stream = torch.cuda.Stream(device=dev, priority=-1)
         _loss_stream.wait_stream(cur)
         with torch.cuda.stream(_loss_stream):
             L.call("vmmt_kl_fwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(stats[3:4]), B, Z, stream())
