@@ -33,6 +33,9 @@ unsigned long long vmmt_launch_count(void);
 /* 0 = auto (tcgen05 TF32 tensor-core GEMM where eligible), 1 = exact-fp32 SIMT GEMM everywhere. */
 void vmmt_set_gemm_mode(int mode);
 int vmmt_get_gemm_mode(void);
+/* 1: the GEMMs launched next are background work (weight gradients on a low-priority side stream): one tile per CTA
+ * instead of the persistent per-SM tile loop, so that SMs free up for critical-path kernels between tiles.  Host flag. */
+void vmmt_gemm_set_background(int on);
 
 /* C[M,N] (ldc) = act(op(A) op(B) + bias[N]) (+C if accumulate).
  * a_kmajor: A stored [M,K] (1) or [K,M] (0);  b_kmajor: B stored [N,K] (1, nn.Linear weight) or [K,N] (0).
@@ -177,6 +180,9 @@ int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, i
                         size_t workspace_bytes, void* stream);
 
 /* ---- optimiser: global-norm clip + Adam on flat buffers (Optim.py:69-70,94-96) */
+/* model.zero_grad() (TrainerMultimodal.py:627-628) on the flat gradient buffer with at most max_blocks resident blocks
+ * (0 = one per SM), so that it can run beside latency-critical kernels without starving them of SM slots or HBM. */
+int vmmt_fill_zero(float* p, int64_t n, int max_blocks, void* stream);
 size_t vmmt_sqnorm_workspace_bytes(void);
 int vmmt_sqnorm(const float* g, int64_t n, float* out1, int accumulate, void* workspace, void* stream);
 int vmmt_adam_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -42,6 +42,7 @@ SIGNATURES = {
     "vmmt_launch_count": (C.c_ulonglong, []),
     "vmmt_set_gemm_mode": (None, [I]),
     "vmmt_get_gemm_mode": (I, []),
+    "vmmt_gemm_set_background": (None, [I]),
     "vmmt_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P]),
     "vmmt_gemm_dual": (I, [P, L, P, L, I, P, L, P, L, I, P, L, I, I, P, I, P]),
     "vmmt_embedding_fwd": (I, [P, L, P, I, P, P]),
@@ -77,6 +78,7 @@ SIGNATURES = {
     "vmmt_generator_topk_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_generator_topk_supported": (I, [P, P, I, I, I]),
     "vmmt_generator_topk": (I, [P, P, P, I, I, I, I, P, SZ, P]),
+    "vmmt_fill_zero": (I, [P, L, I, P]),
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),
     "vmmt_adam_clip_step": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),

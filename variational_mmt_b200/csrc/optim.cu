@@ -81,7 +81,29 @@ adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// Zero fill on a FEW resident blocks (grid-stride float4 stores).  A plain memset of the 171 MB gradient buffer floods
+// every SM with thousands of short blocks: fine alone, but beside the encoder recurrences it keeps their thread-block
+// clusters from being placed, and beside the generator GEMM it takes a third of the HBM bandwidth.  `max_blocks`
+// light blocks (one per SM, 256 threads) co-reside with anything and spread the same bytes over a longer window.
+__global__ void __launch_bounds__(256)
+fill_zero_kernel(float4* __restrict__ p, int64_t n4, float* __restrict__ tail, int ntail) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) p[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
+}
+
 }  // namespace
+
+extern "C" int vmmt_fill_zero(float* p, int64_t n, int max_blocks, void* stream) {
+  if (n <= 0) return VMMT_OK;
+  VMMT_REQUIRE(((uintptr_t)p & 15) == 0, "fill_zero: buffer must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  int nblk = max_blocks > 0 ? max_blocks : vmmt_num_sms();
+  if ((int64_t)nblk * 256 > n4 && n4 > 0) nblk = ceil_div(n4, 256);
+  if (nblk < 1) nblk = 1;
+  fill_zero_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>((float4*)p, n4, p + n4 * 4, (int)(n - n4 * 4));
+  return vmmt_check_launch("fill_zero");
+}
 
 extern "C" size_t vmmt_sqnorm_workspace_bytes(void) { return 1024 * sizeof(double); }
 

@@ -72,9 +72,15 @@ class FlatParamsMixin:
     def flatten_parameters(self):
         return flatten_parameters(self)
 
-    def zero_grad(self, set_to_none=False):
+    def zero_grad(self, set_to_none=False, max_blocks=None):
+        """``max_blocks``: zero the flat gradient buffer with that many resident blocks (vmmt_fill_zero) instead of a
+        full-width memset -- for callers that overlap it with latency-critical work (GraphedTrainStep)."""
         if self._flat_grads is not None and not set_to_none:
-            self._flat_grads.zero_()
+            if max_blocks is not None and self._flat_grads.is_cuda:
+                from . import _lib as L
+                L.call("vmmt_fill_zero", L.fptr(self._flat_grads), self._flat_grads.numel(), int(max_blocks), L.stream())
+            else:
+                self._flat_grads.zero_()
             return
         if self._flat_grads is not None:
             raise RuntimeError("zero_grad(set_to_none=True) would detach the flat gradient views")

@@ -125,11 +125,13 @@ class _OnSide(object):
                 pass                                   # not inside a backward pass: the caller joins explicitly
         self.ctx = torch.cuda.stream(side)
         self.ctx.__enter__()
+        L.lib.vmmt_gemm_set_background(1)
         _side["dirty"] = True
         return self
 
     def __exit__(self, *exc):
         if self.active:
+            L.lib.vmmt_gemm_set_background(0)
             self.ctx.__exit__(*exc)
         return False
 
@@ -653,6 +655,24 @@ class VILossFn(Function):
         M, H = out2d.shape
         V = ctx.gen_w.shape[0]
         gs = dloss.reshape(1).contiguous()                     # device scalar: no host sync
+        # KL / image gradients first, on the loss stream: they are tiny and independent of the generator's backward, and the
+        # decoder-output gradient below must not queue behind them (it is the backward pass's critical path)
+        B, Z = mu_q.shape
+        dmq, dsq = torch.empty_like(mu_q), torch.empty_like(sd_q)
+        dmp = torch.empty_like(mu_q) if mu_p is not None else None
+        dsp = torch.empty_like(mu_q) if mu_p is not None else None
+        D = img_loc.shape[1]
+        dloc = torch.empty_like(img_loc)
+        cur = torch.cuda.current_stream(dev)
+        global _loss_stream
+        if _loss_stream is None or _loss_stream.device != dev:
+            _loss_stream = torch.cuda.Stream(device=dev, priority=-1)
+        _loss_stream.wait_stream(cur)
+        with torch.cuda.stream(_loss_stream):
+            L.call("vmmt_kl_bwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(dmq), fptr(dsq), fptr(dmp),
+                   fptr(dsp), fptr(gs), float(cfg["kl_weight"]), B, Z, stream())
+            L.call("vmmt_image_loss_bwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(dloc), fptr(gs), 1.0,
+                   int(cfg.get("legacy_image_grad", True)), B, D, stream())
         dx = torch.empty(M, H, device=dev, dtype=torch.float32)
         wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
@@ -661,16 +681,7 @@ class VILossFn(Function):
         with on_side(ws, out2d):                               # generator weight gradient: off the critical path
             L.call("vmmt_generator_nll_wgrad", fptr(out2d), fptr(ws), M, H, V, fptr(grad_buf(ctx.gen_w)),
                    fptr(grad_buf(ctx.gen_b)), stream())
-        B, Z = mu_q.shape
-        dmq, dsq = torch.empty_like(mu_q), torch.empty_like(sd_q)
-        dmp = torch.empty_like(mu_q) if mu_p is not None else None
-        dsp = torch.empty_like(mu_q) if mu_p is not None else None
-        L.call("vmmt_kl_bwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(dmq), fptr(dsq), fptr(dmp),
-               fptr(dsp), fptr(gs), float(cfg["kl_weight"]), B, Z, stream())
-        D = img_loc.shape[1]
-        dloc = torch.empty_like(img_loc)
-        L.call("vmmt_image_loss_bwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(dloc), fptr(gs), 1.0,
-               int(cfg.get("legacy_image_grad", True)), B, D, stream())
+        cur.wait_stream(_loss_stream)
         return dx, None, None, None, dmq, dsq, dmp, dsp, dloc, None, None
 
 
