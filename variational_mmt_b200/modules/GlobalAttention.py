@@ -34,8 +34,7 @@ class GlobalAttention(nn.Module):
         dim = self.dim
         qp = ops.linear(q, self.linear_in.weight) if self.attn_type == "general" else q
         cvec, align = ops.AttentionCoreFn.apply(qp, context, context_lengths)
-        part = ops.linear(cvec, self.linear_out.weight, cols=(0, dim))
-        attn_h = ops.linear(q, self.linear_out.weight, act=ops.ACT_TANH, cols=(dim, 2 * dim), addend=part)
+        attn_h = ops.dual_linear(cvec, q, self.linear_out.weight, act=ops.ACT_TANH)     # tanh(linear_out([c ; q]))
         return attn_h, align
 
     def forward(self, input, context, context_lengths=None, coverage=None):

@@ -311,6 +311,58 @@ class LinearFn(Function):
         return None, dx, None, None, None, None, dadd
 
 
+class DualLinearFn(Function):
+    """y = act([x1 ; x2] W^T) for W = [N, K1 + K2] without materialising the concatenation: ONE dual-operand GEMM forward
+    (vmmt_gemm_dual), ONE input-gradient GEMM [dx1 ; dx2] = dpre W backward (GlobalAttention.py:187-190: linear_out over
+    cat([c, q])), weight gradients per column block on a side stream."""
+
+    @staticmethod
+    def forward(ctx, anchor, x1, x2, weight, act):
+        weight = weight.t
+        K1, K2 = x1.shape[-1], x2.shape[-1]
+        N = weight.shape[0]
+        assert weight.shape[1] == K1 + K2
+        a1 = x1.reshape(-1, K1)
+        a2 = x2.reshape(-1, K2)
+        a1 = a1 if a1.stride(-1) == 1 and (a1.shape[0] == 1 or a1.stride(0) >= K1) else a1.contiguous()
+        a2 = a2 if a2.stride(-1) == 1 and (a2.shape[0] == 1 or a2.stride(0) >= K2) else a2.contiguous()
+        M = a1.shape[0]
+        y = torch.empty(M, N, device=x1.device, dtype=torch.float32)
+        gemm_dual(a1, weight[:, :K1], a2, weight[:, K1:], y, M, N, K1, K2, act=act)
+        ctx.save_for_backward(a1, a2, y)
+        ctx.weight, ctx.act, ctx.shapes = weight, act, (x1.shape, x2.shape)
+        return y.view(*x1.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a1, a2, y = ctx.saved_tensors
+        weight, act = ctx.weight, ctx.act
+        M, K1 = a1.shape
+        K2 = a2.shape[1]
+        N = weight.shape[0]
+        dy = dy.reshape(M, N).contiguous()
+        if act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            L.call("vmmt_act_bwd", fptr(dy), fptr(y), fptr(dpre), dy.numel(), act, stream())
+        else:
+            dpre = dy
+        dx = torch.empty(M, K1 + K2, device=dy.device, dtype=torch.float32)
+        gemm(dpre, weight, dx, M, K1 + K2, N, b_kmajor=False)                      # [dx1 ; dx2] = dpre W, one launch
+        with on_side(dpre, a1, a2):
+            if weight.requires_grad:
+                gw = grad_buf(weight)
+                gemm(dpre, a1, gw[:, :K1], N, K1, M, a_kmajor=False, b_kmajor=False, accumulate=1)
+                gemm(dpre, a2, gw[:, K1:], N, K2, M, a_kmajor=False, b_kmajor=False, accumulate=1)
+        s1, s2 = ctx.shapes
+        dx1 = dx[:, :K1].reshape(s1) if ctx.needs_input_grad[1] else None
+        dx2 = dx[:, K1:].reshape(s2) if ctx.needs_input_grad[2] else None
+        return None, dx1, dx2, None, None
+
+
+def dual_linear(x1, x2, weight, act=ACT_NONE):
+    return DualLinearFn.apply(_anchor(x1.device), x1, x2, _P(weight), act)
+
+
 def linear(x, weight, bias=None, act=ACT_NONE, cols=None, addend=None):
     return LinearFn.apply(_anchor(x.device), x, _P(weight), _P(bias), act, cols, addend)
 
