@@ -281,9 +281,13 @@ __device__ __forceinline__ void wv_tile(const float (*Ws)[TT], const float* __re
 __global__ void __launch_bounds__(TILE_THREADS)
 attn_fwd_tiled_kernel(const float* __restrict__ qp, const float* __restrict__ ctx, const int64_t* __restrict__ lengths,
                       float* __restrict__ align, float* __restrict__ cvec, int T, int B, int S, int H, int ntile) {
-  __shared__ float Xs[TT][KC + 1];
-  __shared__ float Cs[SMAX][KC + 1];
-  __shared__ __align__(16) float Ws[SMAX][TT];
+  // dynamic shared memory sized by the source length (rounded up to 32 positions): 8 KB at S <= 32 instead of the 27 KB
+  // of the S = 128 worst case, so that these CTAs still fit beside a 208 KB GEMM CTA on the same SM
+  extern __shared__ __align__(16) float att_smem[];
+  const int srows = ((S + 31) / 32) * 32;
+  float (*Xs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(att_smem);
+  float (*Cs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(att_smem + TT * (KC + 1));
+  float (*Ws)[TT] = reinterpret_cast<float (*)[TT]>(att_smem + TT * (KC + 1) + srows * (KC + 1));
   const int b = blockIdx.x / ntile, t0 = (blockIdx.x % ntile) * TT;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int len = lengths ? min((int)lengths[b], S) : S;
@@ -308,7 +312,7 @@ attn_fwd_tiled_kernel(const float* __restrict__ qp, const float* __restrict__ ct
     for (int jj = 0; jj < 4; ++jj) {
       const int j = tx + 32 * jj;
       const float a = acc[i][jj] * inv;
-      Ws[j][tt] = a;
+      if (j < srows) Ws[j][tt] = a;
       if (t < T && j < S) align[((size_t)t * B + b) * S + j] = a;
     }
   }
@@ -321,9 +325,13 @@ __global__ void __launch_bounds__(TILE_THREADS)
 attn_bwd_query_tiled_kernel(const float* __restrict__ dc, const float* __restrict__ ctx, const float* __restrict__ align,
                             const int64_t* __restrict__ lengths, float* __restrict__ dscore, float* __restrict__ dqp,
                             int T, int B, int S, int H, int ntile) {
-  __shared__ float Xs[TT][KC + 1];
-  __shared__ float Cs[SMAX][KC + 1];
-  __shared__ __align__(16) float Ws[SMAX][TT];
+  // dynamic shared memory sized by the source length (rounded up to 32 positions): 8 KB at S <= 32 instead of the 27 KB
+  // of the S = 128 worst case, so that these CTAs still fit beside a 208 KB GEMM CTA on the same SM
+  extern __shared__ __align__(16) float att_smem[];
+  const int srows = ((S + 31) / 32) * 32;
+  float (*Xs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(att_smem);
+  float (*Cs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(att_smem + TT * (KC + 1));
+  float (*Ws)[TT] = reinterpret_cast<float (*)[TT]>(att_smem + TT * (KC + 1) + srows * (KC + 1));
   const int b = blockIdx.x / ntile, t0 = (blockIdx.x % ntile) * TT;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int len = lengths ? min((int)lengths[b], S) : S;
@@ -344,7 +352,7 @@ attn_bwd_query_tiled_kernel(const float* __restrict__ dc, const float* __restric
     for (int jj = 0; jj < 4; ++jj) {
       const int j = tx + 32 * jj;
       const float ds = a[jj] * (da[i][jj] - dot);
-      Ws[j][tt] = ds;
+      if (j < srows) Ws[j][tt] = ds;
       if (t < T && j < S) dscore[((size_t)t * B + b) * S + j] = ds;
     }
   }
@@ -406,6 +414,11 @@ attn_bwd_ctx_tiled_kernel(const float* __restrict__ dc, const float* __restrict_
   }
 }
 
+size_t tiled_smem_bytes(int S) {
+  const int srows = ((S + 31) / 32) * 32;
+  return (size_t)(TT * (KC + 1) + srows * (KC + 1) + srows * TT) * sizeof(float);
+}
+
 }  // namespace
 
 extern "C" int vmmt_attention_fwd(const float* qp, const float* ctx, const int64_t* lengths,
@@ -415,8 +428,8 @@ extern "C" int vmmt_attention_fwd(const float* qp, const float* ctx, const int64
   VMMT_REQUIRE(T >= 1 && B >= 1 && H >= 1, "attention_fwd: bad dims");
   if (T > 1 && !getenv("VMMT_ATTN_WARP")) {          // sequence mode: tiled kernel (one CTA per 16 queries of one row)
     const int ntile = ceil_div(T, TT);
-    attn_fwd_tiled_kernel<<<B * ntile, TILE_THREADS, 0, (cudaStream_t)stream>>>(qp, ctx, lengths, align, cvec, T, B,
-                                                                               S, H, ntile);
+    attn_fwd_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), (cudaStream_t)stream>>>(
+        qp, ctx, lengths, align, cvec, T, B, S, H, ntile);
     return vmmt_check_launch("attn_fwd_tiled_kernel");
   }
   int tsplit = ceil_div(T, ATT_WARPS);
@@ -436,8 +449,8 @@ extern "C" int vmmt_attention_bwd(const float* dcvec, const float* qp, const flo
   if (!getenv("VMMT_ATTN_WARP")) {
     cudaStream_t st = (cudaStream_t)stream;
     const int ntile = ceil_div(T, TT), nk = ceil_div(H, 64);
-    attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, 0, st>>>(dcvec, ctx, align, lengths, dscore_ws, dqp, T, B,
-                                                                    S, H, ntile);
+    attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), st>>>(dcvec, ctx, align, lengths,
+                                                                                      dscore_ws, dqp, T, B, S, H, ntile);
     int rc1 = vmmt_check_launch("attn_bwd_query_tiled_kernel");
     if (rc1) return rc1;
     attn_bwd_ctx_tiled_kernel<<<B * nk, TILE_THREADS, 0, st>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H,
