@@ -51,6 +51,12 @@ class GraphedTrainStep(object):
         self.device = next(model.parameters()).device
         ops.rng_base(self.device)
 
+    def _param_addresses(self):
+        """(parameter, gradient) addresses a captured graph has baked in; they move when Optim.set_parameters re-homes the
+        flat buffers into the NVLink peer segment or the model changes device."""
+        p = next(self.model.parameters())
+        return (p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0)
+
     def _run(self, src, sl, tgt, tl, img, normalization):
         out, attns, _ = self.model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
         # the 171 MB gradient memset runs beside the generator / loss forward (nothing touches a gradient before the
@@ -96,7 +102,7 @@ class GraphedTrainStep(object):
         if self._pool is None:
             self._pool = g.pool()
         self.loss.n_model_updates = n_updates           # the warm-up / capture passes are not model updates
-        self._graphs[key] = (g, static, vec)
+        self._graphs[key] = (g, static, vec, self._param_addresses())
         return self._graphs[key]
 
     def __call__(self, src, src_lengths, tgt, tgt_lengths, img_feats, normalization):
@@ -109,7 +115,10 @@ class GraphedTrainStep(object):
         entry = self._graphs.get(key)
         if entry is None:
             entry = self._capture(key, inputs, normalization)
-        g, static, vec = entry
+        g, static, vec, gen = entry
+        if gen != self._param_addresses():
+            raise RuntimeError("GraphedTrainStep: the parameters were moved to other buffers after this graph was captured "
+                               "(Optim.set_parameters / model.to()): create the GraphedTrainStep after Optim.set_parameters")
         for s, t in zip(static, inputs):
             s.copy_(t, non_blocking=True)
         g.replay()
