@@ -188,6 +188,7 @@ def run_ours(args):
     loss_fn = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
     optim = vm.Optim("adam", 0.002, 5)
     optim.set_parameters(model.parameters())
+    optim.enable_early_exchange(model)                    # N > 1 on one box: loss-side gradients exchanged beside the encoder backward
     n_params = sum(p.numel() for p in model.parameters())
 
     # a ring of different host batches (pinned), one per step modulo NB
@@ -207,7 +208,7 @@ def run_ours(args):
     def to_dev(h):
         return [t.to(dev, non_blocking=True) for t in h]
 
-    graphed = None if args.no_graph else vm.GraphedTrainStep(model, loss_fn, shard_size=shard)
+    graphed = None if args.no_graph else vm.GraphedTrainStep(model, loss_fn, shard_size=shard, optim=optim)
 
     def eager_fwd_bwd(d):
         src, sl, tgt, tl, img = [t.to(dev, non_blocking=True) for t in d]

@@ -63,7 +63,27 @@ def _worker(rank, world, port, out_dir):
     fwd_bwd(batches[rank], norm)
     optim.step()
     torch.cuda.synchronize()
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), g=g_nccl, p=p_nccl, p_peer=optim.flat.cpu().numpy(),
+    p_peer = optim.flat.cpu().numpy()
+    # and with the loss-side gradients (generator, latent / image networks) reduce-scattered early, beside the encoders'
+    # backward pass (Optim.enable_early_exchange): two steps, so that the second one sees the first one's all-gather
+    res = {}
+    for early in (False, True):
+        model, fields = build_cuda_model(cfg, params)
+        model.train()
+        loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+        optim = vm.Optim("adam", 0.002, 5)
+        optim.set_parameters(model.parameters())
+        if early:
+            assert optim.enable_early_exchange(model), "early exchange did not come up"
+            assert 0 < optim._early["begin"] < optim.flat.numel()
+        for _ in range(2):
+            model.zero_grad()
+            fwd_bwd(batches[rank], norm)
+            assert (not early) or optim._early_done, "the backward pass did not fire the early reduce-scatter"
+            optim.step()
+        torch.cuda.synchronize()
+        res[early] = optim.flat.cpu().numpy()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), g=g_nccl, p=p_nccl, p_peer=p_peer, p2=res[False], p2_early=res[True],
              vec=vec.cpu().numpy(), accum=(accum.cpu().numpy() if accum is not None else np.zeros(1)))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
@@ -84,3 +104,6 @@ def test_two_gpu_step_equals_accumulation(tmp_path):
     # so a handful of near-zero gradients may move differently; everything else agrees to rounding
     bad = ~np.isclose(r0["p_peer"], r0["p"], rtol=1e-5, atol=1e-6)
     assert bad.mean() < 1e-4, (int(bad.sum()), float(np.abs(r0["p_peer"] - r0["p"]).max()))
+    assert np.array_equal(r0["p2_early"], r1["p2_early"])                              # split exchange: replicas identical
+    bad = ~np.isclose(r0["p2_early"], r0["p2"], rtol=1e-5, atol=2e-6)                 # and equal to the one-phase exchange
+    assert bad.mean() < 2e-4, (int(bad.sum()), float(np.abs(r0["p2_early"] - r0["p2"]).max()))

@@ -105,3 +105,44 @@ def test_multi_gpu_peer_step_equals_nccl_step(tmp_path, world):
     bad = ~np.isclose(rs[0]["peer"], rs[0]["nccl"], rtol=2e-6, atol=1e-8)
     assert bad.mean() < 1e-5, (int(bad.sum()), float(np.abs(rs[0]["peer"] - rs[0]["nccl"]).max()))
     assert abs(float(rs[0]["peer_sq"]) - float(rs[0]["nccl_sq"])) <= 1e-5 * float(rs[0]["nccl_sq"])
+
+
+def test_split_exchange_world1_equals_replicated_step(cuda_device):
+    """Optim.enable_early_exchange on one GPU (world = 1: the rank is its own peer): the encoder backward fires the
+    early reduce-scatter of the flat buffer's tail, step() exchanges the rest, and two training steps of the real
+    (tiny) model end on the parameters the replicated clip + Adam produces."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import variational_mmt_b200 as vm
+    from gpu_helpers import build_cuda_model, to_device
+    from oracle import synth
+    cfg = synth.TINY
+    params = synth.make_params(cfg, 3435, 0.1)
+    batch = synth.make_batch(cfg, batch_size=6, seed=3, t_force=20)
+    res = {}
+    for mode in ("nccl", "peer", "peer_early"):
+        model, fields = build_cuda_model(cfg, params)
+        model.train()
+        loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+        optim = vm.Optim("adam", 0.002, 5, exchange="nccl" if mode == "nccl" else "peer")
+        optim.set_parameters(model.parameters())
+        if mode == "peer_early":
+            assert optim.enable_early_exchange(model)
+            n, b0 = optim.flat.numel(), optim._early["begin"]
+            names = [k for k, _ in model.named_parameters()]
+            assert 0 < b0 < n and any(k.startswith("generator.") for k in names)
+        d = to_device(batch)
+        for _ in range(2):
+            model.zero_grad()
+            with vm.Normal.inject_noise(d.eps):
+                out, attns, _ = model(d.src, d.tgt_in, d.src_lengths, d.tgt_lengths, d.img_feats)
+            loss.sharded_compute_loss(d, out, attns, 0, d.tgt.size(0), 32, d.batch_size)
+            if mode == "peer_early":
+                assert optim._early_done, "the encoder backward did not fire the early reduce-scatter"
+            optim.step()
+        torch.cuda.synchronize()
+        res[mode] = optim.flat.cpu().numpy()
+        res[mode + "_sq"] = float(optim._sq)
+    for mode in ("peer", "peer_early"):
+        bad = ~np.isclose(res[mode], res["nccl"], rtol=1e-5, atol=2e-6)
+        assert bad.mean() < 2e-4, (mode, int(bad.sum()), float(np.abs(res[mode] - res["nccl"]).max()))
+        assert abs(res[mode + "_sq"] - res["nccl_sq"]) <= 1e-4 * res["nccl_sq"]

@@ -137,10 +137,12 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         self.image_features_projector = None
         self.two_step_image_prediction = False
         self.encoder, self.decoder = encoder, decoder
+        self.encoder.rnn.fires_early_exchange = True
         self.encoder_tgt = kwargs["encoder_tgt"] if self.conditional else None
         if self.encoder_tgt is not None:
             self.encoder_tgt.no_pack_padded_seq = True
             # concurrent source / target encoders (training): 3 + 4 of the ~7 GPC-sized cluster slots of a B200
+            self.encoder_tgt.rnn.fires_early_exchange = True
             self.encoder.rnn.cluster_budget = int(os.environ.get("VMMT_ENC_BUDGET", "3")) or None
             self.encoder_tgt.rnn.cluster_budget = int(os.environ.get("VMMT_TGT_BUDGET", "8")) or None
         self.inf_net_global = kwargs["inf_net_global"]
@@ -160,6 +162,13 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
                 _, tgt_context = self.encoder_tgt(orig_tgt.transpose(0, 1), lengths=None)
                 tgt_context = tgt_context.transpose(0, 1)
         enc_hidden, context = self.encoder(src, lengths)
+        hook = getattr(self, "early_exchange_hook", None)
+        if hook is not None and self.training and torch.is_grad_enabled():
+            # data parallel (Optim.enable_early_exchange): the first encoder-stack backward node to run fires the early
+            # reduce-scatter.  Autograd runs ready nodes in reverse creation order and the encoders are created first, so
+            # by then every module that hangs off the loss rather than off the encoder recurrences (generator, image
+            # head, prior / posterior networks, decoder, attention) has issued its weight gradients.
+            ops.arm_early_exchange(hook)
         if self.conditional:
             ops.join_branch(tgt_context)
         if self.training and dec_state is None and hasattr(self.decoder, "input_projection"):

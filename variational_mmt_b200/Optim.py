@@ -7,6 +7,7 @@ csrc/peer.cu); otherwise one NCCL SUM all-reduce of the flat gradient buffer pre
 ``exchange``: "auto" (peer when torch.distributed is up on CUDA, else none), "peer", "nccl"; the
 environment variable VMMT_DP_EXCHANGE overrides "auto".
 """
+import ctypes
 import os
 
 import torch
@@ -15,6 +16,10 @@ from . import _lib as L
 from ._lib import fptr, stream
 from .flat import flatten_parameters, owner_of, padded_numel
 from . import distributed, ops
+
+
+def ctypes_i64():
+    return ctypes.byref(ctypes.c_int64())
 
 
 class _ParamList(torch.nn.Module):
@@ -38,6 +43,8 @@ class Optim(object):
         self.sync_gradients = True           # all-reduce across ranks when torch.distributed is up
         self.exchange = exchange
         self.peer = None                     # distributed.PeerExchange when the NVLink peer path is active
+        self._early = None                   # early (overlapped) exchange of the tail of the flat buffer, see enable_early_exchange
+        self._early_done = False
 
     def set_parameters(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -82,8 +89,62 @@ class Optim(object):
         self._sq = torch.zeros(1, device=p0.device, dtype=torch.float32)
         self._ws = torch.empty(L.lib.vmmt_sqnorm_workspace_bytes() // 4, device=p0.device, dtype=torch.float32)
 
+    def enable_early_exchange(self, model):
+        """Split the peer exchange in two: the gradients of the latent / image networks and the generator (the tail of
+        the flat buffer, final before the encoders' backward pass starts) are reduce-scattered on their own stream
+        BESIDE the encoder backward; only the remainder is exchanged inside step().  A backward hook on the encoder
+        output (registered by NMTVIModel.forward through ``model.early_exchange_hook``) fires the early phase.
+        Call right after set_parameters (the slice-wise Adam moments are re-partitioned).  Returns True when active."""
+        if self.peer is None or self._step != 0 or os.environ.get("VMMT_DP_OVERLAP", "1") == "0":
+            return False
+        begin = distributed.early_final_begin(model)
+        n = self.flat.numel()
+        if begin is None or begin % 4 or begin <= 0 or begin >= n:
+            return False
+        pe, dev = self.peer, self.flat.device
+        lo, hi = ctypes_i64(), ctypes_i64()
+        cap_b = int(L.lib.vmmt_peer_slice(begin, pe.world, pe.rank, lo, hi))
+        cap_a = int(L.lib.vmmt_peer_slice(n - begin, pe.world, pe.rank, lo, hi))
+        z = lambda k: torch.zeros(max(k, 4), device=dev, dtype=torch.float32)        # noqa: E731
+        self._early = {"begin": begin, "gsum_a": z(cap_a), "m_a": z(cap_a), "v_a": z(cap_a), "gsum_b": z(cap_b),
+                       "m_b": z(cap_b), "v_b": z(cap_b),
+                       "ws_a": torch.empty(L.lib.vmmt_peer_adam_workspace_bytes() // 4, device=dev, dtype=torch.float32),
+                       "stream": torch.cuda.Stream(device=dev, priority=-1)}
+        self.exp_avg = self.exp_avg_sq = self._gsum = None       # replaced by the per-range slices above
+        model.early_exchange_hook = self.early_reduce_scatter
+        torch.cuda.synchronize(dev)
+        return True
+
+    def early_reduce_scatter(self):
+        """Phase 1 of the split exchange (called from the backward hook; no host synchronisation, graph-capturable)."""
+        e, pe = self._early, self.peer
+        cur = torch.cuda.current_stream(self.flat.device)
+        xs = e["stream"]
+        xs.wait_stream(cur)
+        capturing = torch.cuda.is_current_stream_capturing()
+        for st in ops.aux_streams():                         # every weight gradient issued so far
+            if capturing:                                    # helper streams that are not part of this capture hold nothing
+                with torch.cuda.stream(st):                  # of this step (and may not be waited on from inside it)
+                    if not torch.cuda.is_current_stream_capturing():
+                        continue
+            xs.wait_stream(st)
+        n = self.flat.numel()
+        with torch.cuda.stream(xs):
+            L.call("vmmt_peer_reduce_scatter", pe.segments, pe.grad_off, pe.rank, pe.world, e["begin"], n - e["begin"],
+                   fptr(e["gsum_a"]), 1, fptr(e["ws_a"]), stream())
+        self._early_done = True
+
+    def join_early(self):
+        """The current stream waits for the early reduce-scatter (a captured step must join it before the capture ends)."""
+        if self._early is not None and self._early_done:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._early["stream"])
+
     @property
     def exchange_in_use(self):
+        if self.peer is not None and self._early is not None:
+            return ("nvlink p2p reduce-scatter + sharded clip/Adam + all-gather (csrc/peer.cu); tail of the buffer "
+                    "(latent / image networks, generator: %.0f%%) reduce-scattered beside the encoder backward"
+                    % (100.0 * (self.flat.numel() - self._early["begin"]) / self.flat.numel()))
         if self.peer is not None:
             return "nvlink p2p reduce-scatter + sharded clip/Adam + all-gather (csrc/peer.cu)"
         return "nccl all-reduce + replicated clip/Adam" if distributed.is_active() else "single rank"
@@ -104,6 +165,21 @@ class Optim(object):
                            min(self._step ** (-0.5), self._step * self.warmup_steps ** (-1.5))))
         n = self.flat.numel()
         max_norm = float(self.max_grad_norm) if self.max_grad_norm else 0.0
+        if self.peer is not None and self._early is not None:
+            e, pe = self._early, self.peer
+            if not self._early_done:                         # no backward hook fired (eval forward, custom loop): do it here
+                self.early_reduce_scatter()
+            torch.cuda.current_stream(self.flat.device).wait_stream(e["stream"])
+            self._early_done = False
+            b0, sm = e["begin"], stream()
+            hyp = (max_norm, float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._step)
+            L.call("vmmt_peer_reduce_scatter", pe.segments, pe.grad_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]), 0,
+                   fptr(self._pws), sm)
+            L.call("vmmt_peer_adam_allgather", pe.segments, pe.param_off, pe.rank, pe.world, b0, n - b0, fptr(e["gsum_a"]),
+                   fptr(e["m_a"]), fptr(e["v_a"]), fptr(self._sq), 2, *hyp, 1, 0, sm)
+            L.call("vmmt_peer_adam_allgather", pe.segments, pe.param_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]),
+                   fptr(e["m_b"]), fptr(e["v_b"]), None, 2, *hyp, 0, 1, sm)
+            return
         if self.peer is not None:
             pe = self.peer
             L.call("vmmt_peer_adam_step", pe.segments, pe.param_off, pe.grad_off, pe.rank, pe.world, n,

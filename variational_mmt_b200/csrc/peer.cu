@@ -31,8 +31,10 @@ constexpr int kMaxRanks = 16;
 // layout of the signal block at the head of every rank's peer segment (bytes)
 //   [0,   64)   arrive[kMaxRanks]  u32, slot j written by rank j
 //   [64,  68)   epoch              u32, local barrier generation
-//   [128, 256)  norm2[kMaxRanks]   f64, slot j written by rank j (its share of ||g||^2)
-constexpr int kSigBytes = 256;
+//   [128, 256)  norm2[0][kMaxRanks]  f64, slot j written by rank j (its share of ||g||^2 of exchange phase 0)
+//   [256, 384)  norm2[1][kMaxRanks]  same for phase 1 (the early, overlapped reduce-scatter of a sub-range)
+constexpr int kSigBytes = 512;
+constexpr int kNormOff = 128;
 
 struct PeerPtrs {
   void* p[kMaxRanks];
@@ -91,7 +93,7 @@ peer_reduce_scatter_kernel(PeerPtrs grads, int world, int64_t lo4, int64_t hi4,
 
 // Sums the block partials and publishes this rank's share of ||g||^2 into slot `rank` of every peer.
 __global__ void peer_norm_publish_kernel(const double* __restrict__ partial, int nblk, PeerPtrs sig,
-                                         int rank, int world) {
+                                         int rank, int world, int phase) {
   __shared__ double sh[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < nblk; i += blockDim.x) s += partial[i];
@@ -102,7 +104,8 @@ __global__ void peer_norm_publish_kernel(const double* __restrict__ partial, int
     __syncthreads();
   }
   if ((int)threadIdx.x < world) {
-    double* slot = reinterpret_cast<double*>(reinterpret_cast<char*>(sig.p[threadIdx.x]) + 128) + rank;
+    double* slot = reinterpret_cast<double*>(reinterpret_cast<char*>(sig.p[threadIdx.x]) + kNormOff) +
+                   phase * kMaxRanks + rank;
     *reinterpret_cast<volatile double*>(slot) = sh[0];
     __threadfence_system();
   }
@@ -113,12 +116,13 @@ template <int W>
 __global__ void __launch_bounds__(256)
 peer_adam_allgather_kernel(PeerPtrs params, int world, int rank, int64_t lo4, int64_t hi4,
                            const float4* __restrict__ gsum, float4* __restrict__ m4,
-                           float4* __restrict__ v4, const double* __restrict__ norm2,
+                           float4* __restrict__ v4, const double* __restrict__ norm2, int nphase,
                            float* __restrict__ sq_out, float max_norm, float step_size, float b1,
                            float b2, float inv_bc2_sqrt, float eps) {
   const int nw = (W > 0) ? W : world;
   double tot = 0.0;
-  for (int j = 0; j < nw; ++j) tot += norm2[j];
+  for (int ph = 0; ph < nphase; ++ph)                       // fixed order: identical on every rank
+    for (int j = 0; j < nw; ++j) tot += norm2[ph * kMaxRanks + j];
   const float sq = (float)tot;
   if (blockIdx.x == 0 && threadIdx.x == 0 && sq_out) sq_out[0] = sq;
   float coef = 1.f;
@@ -195,42 +199,42 @@ extern "C" int vmmt_peer_barrier(void* const* segments, int rank, int world, voi
 
 extern "C" size_t vmmt_peer_adam_workspace_bytes(void) { return 2048 * sizeof(double); }
 
-extern "C" int64_t vmmt_peer_slice(int64_t n, int world, int rank, int64_t* lo, int64_t* hi) {
+// [*lo, *hi) = the floats of the n-float range starting at `base` that rank `rank` reduces and updates
+static int64_t range_slice(int64_t base, int64_t n, int world, int rank, int64_t* lo, int64_t* hi) {
   const int64_t n4 = n / 4;
   const int64_t per = (n4 + world - 1) / world;
   int64_t a = per * rank, b = per * (rank + 1);
   if (a > n4) a = n4;
   if (b > n4) b = n4;
-  if (lo) *lo = a * 4;
-  if (hi) *hi = b * 4;
+  if (lo) *lo = base + a * 4;
+  if (hi) *hi = base + b * 4;
   return per * 4;                       // capacity (floats) every rank allocates for its slice state
 }
 
-extern "C" int vmmt_peer_adam_step(void* const* segments, size_t param_off, size_t grad_off, int rank,
-                                   int world, int64_t n, float* gsum, float* exp_avg,
-                                   float* exp_avg_sq, float* sqnorm_out, float max_norm, float lr,
-                                   float beta1, float beta2, float eps, int64_t step, void* workspace,
-                                   void* stream) {
+extern "C" int64_t vmmt_peer_slice(int64_t n, int world, int rank, int64_t* lo, int64_t* hi) {
+  return range_slice(0, n, world, rank, lo, hi);
+}
+
+// barrier -> reduce-scatter of the sub-range [begin, begin + n) of the flat gradient buffers (this rank's slice of
+// it) -> this rank's share of ||g||^2 published into norm slot array `phase` (0 or 1) of every peer.
+// Two phases let a step exchange a sub-range EARLY (beside the rest of the backward pass) and the remainder at the end.
+extern "C" int vmmt_peer_reduce_scatter(void* const* segments, size_t grad_off, int rank, int world, int64_t begin,
+                                        int64_t n, float* gsum, int phase, void* workspace, void* stream) {
   VMMT_REQUIRE(segments && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
-               "peer_adam_step: bad rank/world");
-  VMMT_REQUIRE(n > 0 && n % 4 == 0, "peer_adam_step: n must be a positive multiple of 4");
-  VMMT_REQUIRE(param_off % 16 == 0 && grad_off % 16 == 0, "peer_adam_step: offsets must be 16-byte aligned");
-  VMMT_REQUIRE(step >= 1, "peer_adam_step: step must be >= 1");
-  VMMT_REQUIRE((((uintptr_t)gsum | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
-               "peer_adam_step: slice buffers must be 16-byte aligned");
+               "peer_reduce_scatter: bad rank/world");
+  VMMT_REQUIRE(n > 0 && n % 4 == 0 && begin >= 0 && begin % 4 == 0, "peer_reduce_scatter: range must be 16-byte granular");
+  VMMT_REQUIRE(grad_off % 16 == 0 && ((uintptr_t)gsum & 15) == 0, "peer_reduce_scatter: buffers must be 16-byte aligned");
+  VMMT_REQUIRE(phase == 0 || phase == 1, "peer_reduce_scatter: phase must be 0 or 1");
   cudaStream_t s = (cudaStream_t)stream;
-  PeerPtrs sig, grads, params;
+  PeerPtrs sig, grads;
   fill(&sig, segments, world, 0);
   fill(&grads, segments, world, grad_off);
-  fill(&params, segments, world, param_off);
   int64_t lo, hi;
-  vmmt_peer_slice(n, world, rank, &lo, &hi);
+  range_slice(begin, n, world, rank, &lo, &hi);
   const int64_t lo4 = lo / 4, hi4 = hi / 4, cnt4 = hi4 - lo4;
   int rc;
-
   peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
   if ((rc = vmmt_check_launch("peer_barrier"))) return rc;
-
   int nblk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256 * 2);
   const int cap = vmmt_num_sms() * 8;
   if (nblk > cap) nblk = cap;
@@ -248,34 +252,72 @@ extern "C" int vmmt_peer_adam_step(void* const* segments, size_t param_off, size
       peer_reduce_scatter_kernel<0><<<nblk, 256, 0, s>>>(grads, world, lo4, hi4, (float4*)gsum, partial);
   }
   if ((rc = vmmt_check_launch("peer_reduce_scatter"))) return rc;
-  peer_norm_publish_kernel<<<1, 256, 0, s>>>(partial, nblk, sig, rank, world);
-  if ((rc = vmmt_check_launch("peer_norm_publish"))) return rc;
+  peer_norm_publish_kernel<<<1, 256, 0, s>>>(partial, nblk, sig, rank, world, phase);
+  return vmmt_check_launch("peer_norm_publish");
+}
 
-  peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
-  if ((rc = vmmt_check_launch("peer_barrier"))) return rc;
-
+// [barrier ->] clip (total norm = sum over `nphase` slot arrays) + Adam on this rank's slice of [begin, begin + n),
+// new parameters stored into all N parameter buffers [-> barrier].  The barrier before is needed once after the last
+// reduce-scatter of a step, the barrier after once after the last update.
+extern "C" int vmmt_peer_adam_allgather(void* const* segments, size_t param_off, int rank, int world, int64_t begin,
+                                        int64_t n, const float* gsum, float* exp_avg, float* exp_avg_sq,
+                                        float* sqnorm_out, int nphase, float max_norm, float lr, float beta1, float beta2,
+                                        float eps, int64_t step, int barrier_before, int barrier_after, void* stream) {
+  VMMT_REQUIRE(segments && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
+               "peer_adam_allgather: bad rank/world");
+  VMMT_REQUIRE(n > 0 && n % 4 == 0 && begin >= 0 && begin % 4 == 0, "peer_adam_allgather: range must be 16-byte granular");
+  VMMT_REQUIRE(param_off % 16 == 0, "peer_adam_allgather: offsets must be 16-byte aligned");
+  VMMT_REQUIRE(step >= 1 && (nphase == 1 || nphase == 2), "peer_adam_allgather: bad step / nphase");
+  VMMT_REQUIRE((((uintptr_t)gsum | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+               "peer_adam_allgather: slice buffers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  PeerPtrs sig, params;
+  fill(&sig, segments, world, 0);
+  fill(&params, segments, world, param_off);
+  int64_t lo, hi;
+  range_slice(begin, n, world, rank, &lo, &hi);
+  const int64_t lo4 = lo / 4, hi4 = hi / 4, cnt4 = hi4 - lo4;
+  int rc;
+  if (barrier_before) {
+    peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
+    if ((rc = vmmt_check_launch("peer_barrier"))) return rc;
+  }
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  const double* norm2 = reinterpret_cast<const double*>((const char*)segments[rank] + 128);
+  const double* norm2 = reinterpret_cast<const double*>((const char*)segments[rank] + kNormOff);
   const int ablk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256);
   switch (world) {
 #define AD_CASE(W)                                                                                \
   case W:                                                                                         \
     peer_adam_allgather_kernel<W><<<ablk, 256, 0, s>>>(params, world, rank, lo4, hi4, (const float4*)gsum, \
-        (float4*)exp_avg, (float4*)exp_avg_sq, norm2, sqnorm_out, max_norm, step_size, beta1, beta2,     \
+        (float4*)exp_avg, (float4*)exp_avg_sq, norm2, nphase, sqnorm_out, max_norm, step_size, beta1, beta2, \
         inv_bc2_sqrt, eps);                                                                       \
     break;
     AD_CASE(1) AD_CASE(2) AD_CASE(4) AD_CASE(8)
 #undef AD_CASE
     default:
       peer_adam_allgather_kernel<0><<<ablk, 256, 0, s>>>(params, world, rank, lo4, hi4, (const float4*)gsum,
-          (float4*)exp_avg, (float4*)exp_avg_sq, norm2, sqnorm_out, max_norm, step_size, beta1, beta2,
+          (float4*)exp_avg, (float4*)exp_avg_sq, norm2, nphase, sqnorm_out, max_norm, step_size, beta1, beta2,
           inv_bc2_sqrt, eps);
   }
   if ((rc = vmmt_check_launch("peer_adam_allgather"))) return rc;
+  if (barrier_after) {
+    peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
+    return vmmt_check_launch("peer_barrier");
+  }
+  return VMMT_OK;
+}
 
-  peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
-  return vmmt_check_launch("peer_barrier");
+// The whole flat buffer in one go: barrier -> reduce-scatter + norm -> barrier -> clip + Adam + all-gather -> barrier.
+extern "C" int vmmt_peer_adam_step(void* const* segments, size_t param_off, size_t grad_off, int rank,
+                                   int world, int64_t n, float* gsum, float* exp_avg,
+                                   float* exp_avg_sq, float* sqnorm_out, float max_norm, float lr,
+                                   float beta1, float beta2, float eps, int64_t step, void* workspace,
+                                   void* stream) {
+  int rc = vmmt_peer_reduce_scatter(segments, grad_off, rank, world, 0, n, gsum, 0, workspace, stream);
+  if (rc) return rc;
+  return vmmt_peer_adam_allgather(segments, param_off, rank, world, 0, n, gsum, exp_avg, exp_avg_sq, sqnorm_out, 1,
+                                  max_norm, lr, beta1, beta2, eps, step, 1, 1, stream);
 }

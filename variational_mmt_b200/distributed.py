@@ -84,6 +84,26 @@ def all_reduce_gradients(flat_grads):
     return flat_grads
 
 
+def early_final_begin(model):
+    """Offset (floats) in the model's flat buffers from which on every parameter belongs to the latent / image networks or
+    the generator -- the modules whose gradients are final BEFORE the encoders' backward pass starts (they hang off
+    the loss, not off the recurrences).  They are registered last (onmt/Models.py:737-760 order; the generator is
+    attached by the constructor), so they form the tail of the flat buffer.  None when that does not hold."""
+    early = ("inf_net_global.", "gen_net_global.", "inf_net_image.", "generator.")
+    off, begin, seen = 0, None, set()
+    for name, p in model.named_parameters():
+        if id(p) in seen:
+            continue
+        seen.add(id(p))
+        if name.startswith(early):
+            if begin is None:
+                begin = off
+        elif begin is not None:
+            return None                       # a late-final parameter after the first early one: no contiguous tail
+        off += ((p.numel() + 3) // 4) * 4
+    return begin if begin else None
+
+
 def reduce_statistics(vec):
     """SUM over ranks of a VIStatistics vector {nmt_loss, n_words, n_correct, kl, img, cos, kl_after, elbo}
     (reporting only; returns a new tensor)."""

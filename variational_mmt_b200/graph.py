@@ -38,10 +38,11 @@ class GraphedTrainStep(object):
     Inputs may live on the host (pinned) or on the device; they are copied into the graph's static buffers.
     """
 
-    def __init__(self, model, loss_compute, shard_size=32, max_graphs=128):
+    def __init__(self, model, loss_compute, shard_size=32, max_graphs=128, optim=None):
         assert not loss_compute.use_kl_annealing, \
             "KL annealing changes a host-side weight every update: use the eager path"
         self.model, self.loss = model, loss_compute
+        self.optim = optim               # told after every replay that the captured early gradient exchange has run
         self.shard_size, self.max_graphs = shard_size, max_graphs
         self._graphs = {}
         self._pool = None
@@ -71,6 +72,8 @@ class GraphedTrainStep(object):
         self.loss.before_backward = lambda: cur.wait_stream(self._zero_stream)
         st = self.loss.sharded_compute_loss(_Batch(tgt, tgt.size(1)), out, attns, 0, tgt.size(0),
                                             self.shard_size, normalization)
+        if self.optim is not None and getattr(self.optim, "_early", None) is not None:
+            self.optim.join_early()      # the early reduce-scatter forked inside the backward pass rejoins the step here
         return st._vec
 
     def _capture(self, key, inputs, normalization):
@@ -122,5 +125,7 @@ class GraphedTrainStep(object):
         for s, t in zip(static, inputs):
             s.copy_(t, non_blocking=True)
         g.replay()
+        if self.optim is not None and getattr(self.optim, "_early", None) is not None:
+            self.optim._early_done = True          # the graph contains Optim.early_reduce_scatter (fired in its backward)
         self.loss.n_model_updates += 1
         return vec

@@ -22,6 +22,7 @@ class LSTM(nn.Module):
         self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
         self.dropout, self.bidirectional = float(dropout), bidirectional
         self.cluster_budget = None       # cap on clusters per recurrence launch (set when two stacks run concurrently)
+        self.fires_early_exchange = False   # encoder stacks: their backward marks the point where the loss-side gradients are final
         ndir = 2 if bidirectional else 1
         k = 1.0 / math.sqrt(hidden_size)
         for l in range(num_layers):
@@ -57,7 +58,8 @@ class LSTM(nn.Module):
                    # weight gradients of a bidirectional stack (the target encoder) and of a unidirectional one (source
                    # encoder / decoder) go to different side streams: the two encoders' backward passes run
                    # concurrently and their last weight-gradient blocks are the tail of the step
-                   "side_lane": 1 if self.bidirectional else 0}
+                   "side_lane": 1 if self.bidirectional else 0,
+                   "fires_early_exchange": self.fires_early_exchange}
             x, hT, cT = ops.lstm_layer(x, h0, c0, in_bias if l == 0 else None, lengths, cfg, self._weights(l))
             hs.append(hT)
             cs.append(cT)

@@ -201,6 +201,29 @@ def join_branch(*tensors, lane=0):
             t.record_stream(cur)
 
 
+_early_cb = [None]
+
+
+def arm_early_exchange(fn):
+    """``fn`` runs once, at the start of the first encoder-stack backward node of the current backward pass."""
+    _early_cb[0] = fn
+
+
+def _fire_early_exchange():
+    fn, _early_cb[0] = _early_cb[0], None
+    if fn is not None:
+        fn()
+
+
+def aux_streams():
+    """Every helper stream this module has created (side lanes, branch lanes, loss stream): what a consumer of ALL the
+    gradients issued so far has to wait for."""
+    out = list(_side["streams"]) + list(_branch["streams"].values())
+    if _loss_stream is not None:
+        out.append(_loss_stream)
+    return out
+
+
 def set_branch_enabled(flag):
     _branch["enabled"] = bool(flag)
 
@@ -430,6 +453,7 @@ class LSTMLayerFn(Function):
             ctx.gx_given = gx_given
             ctx.cluster_budget = int(cfg.get("cluster_budget") or 0)
             ctx.side_lane = cfg.get("side_lane")
+            ctx.fires_early_exchange = bool(cfg.get("fires_early_exchange"))
         ctx.set_materialize_grads(False)
         return out, hT, cT
 
@@ -438,6 +462,8 @@ class LSTMLayerFn(Function):
         x, out, gates, cs, h0, c0, rowbias, lengths = ctx.saved_tensors
         weights = ctx.weights
         ndir, T, N, In, Hd, c0c, c1c = ctx.cfg
+        if ctx.fires_early_exchange:
+            _fire_early_exchange()
         gx_given = ctx.gx_given
         dev = out.device
         dout = dout.contiguous() if dout is not None else None
