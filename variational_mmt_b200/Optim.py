@@ -115,12 +115,17 @@ class Optim(object):
         torch.cuda.synchronize(dev)
         return True
 
-    def early_reduce_scatter(self):
-        """Phase 1 of the split exchange (called from the backward hook; no host synchronisation, graph-capturable)."""
+    def early_reduce_scatter(self, after_event=None):
+        """Phase 1 of the split exchange (called from the first encoder backward node; no host synchronisation,
+        graph-capturable).  ``after_event``: what was on the calling stream when that node started (the node's own
+        recurrence kernel, already launched, is NOT waited for)."""
         e, pe = self._early, self.peer
         cur = torch.cuda.current_stream(self.flat.device)
         xs = e["stream"]
-        xs.wait_stream(cur)
+        if after_event is not None:
+            xs.wait_event(after_event)
+        else:
+            xs.wait_stream(cur)
         capturing = torch.cuda.is_current_stream_capturing()
         for st in ops.aux_streams():                         # every weight gradient issued so far
             if capturing:                                    # helper streams that are not part of this capture hold nothing

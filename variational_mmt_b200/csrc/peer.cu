@@ -236,7 +236,9 @@ extern "C" int vmmt_peer_reduce_scatter(void* const* segments, size_t grad_off, 
   peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
   if ((rc = vmmt_check_launch("peer_barrier"))) return rc;
   int nblk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256 * 2);
-  const int cap = vmmt_num_sms() * 8;
+  // phase 1 runs BESIDE the encoders' backward recurrences: two light blocks per SM leave room for their thread-block
+  // clusters (a grid that fills every SM delays the cluster placement by its whole duration); phase 0 has the GPU alone
+  const int cap = vmmt_num_sms() * (phase == 1 ? 2 : 8);
   if (nblk > cap) nblk = cap;
   if (nblk > 2048) nblk = 2048;
   if (nblk < 1) nblk = 1;

@@ -209,10 +209,10 @@ def arm_early_exchange(fn):
     _early_cb[0] = fn
 
 
-def _fire_early_exchange():
+def _fire_early_exchange(after_event=None):
     fn, _early_cb[0] = _early_cb[0], None
     if fn is not None:
-        fn()
+        fn(after_event)
 
 
 def aux_streams():
@@ -462,8 +462,10 @@ class LSTMLayerFn(Function):
         x, out, gates, cs, h0, c0, rowbias, lengths = ctx.saved_tensors
         weights = ctx.weights
         ndir, T, N, In, Hd, c0c, c1c = ctx.cfg
-        if ctx.fires_early_exchange:
-            _fire_early_exchange()
+        # encoder stacks (data parallel): everything issued before this node is what the early gradient exchange needs; the
+        # exchange itself is launched AFTER this node's recurrence kernel, so that the recurrence's clusters are placed first
+        early_ev = torch.cuda.current_stream().record_event() if (ctx.fires_early_exchange and _early_cb[0] is not None) \
+            else None
         gx_given = ctx.gx_given
         dev = out.device
         dout = dout.contiguous() if dout is not None else None
@@ -491,6 +493,8 @@ class LSTMLayerFn(Function):
         L.lib.vmmt_lstm_set_cluster_budget(ctx.cluster_budget)
         L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
         L.lib.vmmt_lstm_set_cluster_budget(0)
+        if early_ev is not None:
+            _fire_early_exchange(early_ev)
         x2 = x.view(T * N, In) if not gx_given else None
         dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) \
             if (ctx.needs_input_grad[1] and not gx_given) else None
