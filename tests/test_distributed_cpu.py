@@ -91,3 +91,38 @@ def test_two_rank_step_equals_accum_count_two(tmp_path):
             dw = np.abs(g["w"] - np.asarray(params["decoder.attn.linear_in.weight"]))
             assert (dw > 1e-6).mean() < 0.01 and dw.max() <= 2.1 * 0.002 * (step + 1)
         assert np.array_equal(got[0]["w"], got[1]["w"])   # replicas stay bit-identical
+
+
+def test_early_final_range_is_the_tail_of_the_flat_buffer():
+    """distributed.early_final_begin: the latent / image networks and the generator (gradients final before the
+    encoders' backward starts) form the tail of the flat parameter buffer, for both the conditional and fixed prior."""
+    import pytest
+    try:
+        import variational_mmt_b200 as vm
+        from variational_mmt_b200 import synthetic, distributed as D
+    except ImportError as e:
+        pytest.skip(str(e))
+    early = ("inf_net_global.", "gen_net_global.", "inf_net_image.", "generator.")
+    for cond in (True, False):
+        opt = synthetic.make_opt(emb=32, hidden=64, z_dim=24, conditional=cond, dropout=0.0)
+        model = vm.make_vi_model_mmt(opt, synthetic.make_fields(120, 150), gpu=False)
+        begin = D.early_final_begin(model)
+        off, seen, first = 0, set(), None
+        for name, p in model.named_parameters():
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            if name.startswith(early) and first is None:
+                first = off
+            assert name.startswith(early) == (first is not None), name        # nothing late-final after the first early one
+            off += ((p.numel() + 3) // 4) * 4
+        assert begin == first and 0 < begin < off and begin % 4 == 0
+        flat = model._flat_params
+        assert flat is not None and flat.numel() == off                       # same padding rule as flat.flatten_parameters
+
+    class Odd(torch.nn.Module):                                               # an early module NOT at the tail: no split
+        def __init__(self):
+            super().__init__()
+            self.generator = torch.nn.Linear(4, 4)
+            self.encoder = torch.nn.Linear(4, 4)
+    assert D.early_final_begin(Odd()) is None
