@@ -61,6 +61,9 @@ class Optim(object):
             mode = os.environ.get("VMMT_DP_EXCHANGE", "auto")
         if mode == "auto":
             mode = "peer" if (distributed.is_active() and p0.is_cuda and self.method == "adam") else "nccl"
+        if mode == "peer" and (self.method != "adam" or not p0.is_cuda):
+            raise ValueError("exchange='peer' fuses the gradient exchange into the CUDA clip+Adam kernels: it needs "
+                             "method='adam' and parameters on a CUDA device")
         if mode == "peer" and self.peer is None:
             # move the flat buffers into the cudaIpc segment every peer maps (before any CUDA-graph capture)
             owner = owner_of(p0)
@@ -92,9 +95,12 @@ class Optim(object):
     def enable_early_exchange(self, model):
         """Split the peer exchange in two: the gradients of the latent / image networks and the generator (the tail of
         the flat buffer, final before the encoders' backward pass starts) are reduce-scattered on their own stream
-        BESIDE the encoder backward; only the remainder is exchanged inside step().  A backward hook on the encoder
-        output (registered by NMTVIModel.forward through ``model.early_exchange_hook``) fires the early phase.
-        Call right after set_parameters (the slice-wise Adam moments are re-partitioned).  Returns True when active."""
+        BESIDE the encoder backward; only the remainder is exchanged inside step().  The first encoder-stack backward
+        node of a backward pass fires the early phase (NMTVIModel.forward arms it through ``model.early_exchange_hook``).
+        Call right after set_parameters (the slice-wise Adam moments are re-partitioned).  Assumes ONE backward pass per
+        step(): with gradient accumulation over several backward passes the tail is not final when the first pass
+        reaches the encoders -- leave it disabled there.  Returns True when active (False: single rank, NCCL exchange,
+        VMMT_DP_OVERLAP=0, or a model whose loss-side modules are not the tail of the flat buffer)."""
         if self.peer is None or self._step != 0 or os.environ.get("VMMT_DP_OVERLAP", "1") == "0":
             return False
         begin = distributed.early_final_begin(model)
@@ -158,7 +164,11 @@ class Optim(object):
         self.lr = lr
 
     def grad_norm(self):
-        """Global L2 norm of the (all-reduced) gradient as a device scalar tensor."""
+        """Global L2 norm of the (all-reduced) gradient as a device scalar tensor.  With the peer exchange the summed
+        gradient never exists in one place: the value is the norm the last step() clipped with (before any step: the
+        norm of this rank's own gradients)."""
+        if self.peer is not None and self._step > 0:
+            return self._sq.sqrt()
         L.call("vmmt_sqnorm", fptr(self.gflat), self.gflat.numel(), fptr(self._sq), 0, fptr(self._ws), stream())
         return self._sq.sqrt()
 
