@@ -71,3 +71,56 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def _header_prototypes():
+    """{name: (return type text, [parameter type texts])} parsed from include/vmmt.h."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(vmmt_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[name] = (ret, plist)
+    return protos
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Arity and pointer-ness / width class of every ctypes signature against the C prototype: a mismatch here is a
+    silent stack corruption on the GPU box."""
+    _lib_path()
+    from variational_mmt_b200 import _lib
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+
+    def kind(ctype_text):
+        t = ctype_text
+        if "*" in t:
+            return "ptr"
+        t = re.sub(r"\b(const|unsigned|[a-z_][a-z0-9_]*)$", lambda mm: mm.group(0), t)     # keep the text, drop nothing
+        words = [w for w in re.split(r"\s+", t) if w]
+        words = words[:-1] if len(words) > 1 and words[-1] not in ("int", "float", "long", "size_t", "int64_t", "uint64_t") \
+            else words                                                                    # drop the parameter name
+        base = " ".join(w for w in words if w != "const")
+        return {"int": "i32", "float": "f32", "int64_t": "i64", "uint64_t": "i64", "size_t": "i64", "long long": "i64",
+                "unsigned long long": "i64", "void": "void"}.get(base, base)
+
+    cmap = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "i32", ctypes.c_int64: "i64",
+            ctypes.c_uint64: "i64", ctypes.c_size_t: "i64", ctypes.c_float: "f32", ctypes.c_ulonglong: "i64", None: "void"}
+    bad = []
+    for name, (ret, plist) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        if len(args) != len(plist):
+            bad.append(f"{name}: {len(plist)} parameters in the header, {len(args)} in _lib.SIGNATURES")
+            continue
+        for i, (a, ptxt) in enumerate(zip(args, plist)):
+            want = kind(ptxt)
+            got = "ptr" if (isinstance(a, type) and issubclass(a, ctypes._Pointer)) else cmap.get(a, "?")
+            if want != got:
+                bad.append(f"{name} arg {i} ('{ptxt}'): header {want}, ctypes {got}")
+        want_r = kind(ret)
+        got_r = cmap.get(res, "?")
+        if want_r != got_r:
+            bad.append(f"{name} return ('{ret}'): header {want_r}, ctypes {got_r}")
+    assert not bad, "\n".join(bad)
