@@ -38,7 +38,8 @@ namespace {
 
 constexpr int UC = 32;                 // hidden units per CTA
 constexpr int NP = 16;                 // batch columns per cluster (MMA N)
-constexpr int THREADS = 160;           // warps 0-3: epilogue / cell owners, warp 4: MMA issuer
+constexpr int EW = 8;                  // epilogue / cell-owner warps: warp w drains TMEM lane quadrant w & 3
+constexpr int THREADS = 32 * (EW + 1); // + warp EW: MMA issuer
 constexpr float DG_SCALE = 4096.0f;    // backward: dG enters the MMA as fp16 hi + lo of dG * 2^12
 constexpr uint32_t TMEM_COLS = 512;    // whole tensor memory: the allocation then starts at column 0
 constexpr uint32_t TMEM_D = 256;       // accumulators; columns [0,256) hold the weight slice
@@ -86,6 +87,11 @@ __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster, uint3
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
+// 16-byte store into another CTA's shared memory; its completion counts 16 tx bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(dst_cluster), "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
@@ -125,13 +131,54 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// issue-only TMEM loads (the caller waits once for all of them)
+__device__ __forceinline__ void tmem_ld_x4_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_x8_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_x16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.mma kind::f16, A from TMEM, B through a shared-memory descriptor given as its two 32-bit halves (the issue
+// loop only ever advances the low half: start address >> 4)
+__device__ __forceinline__ void umma_f16_ts2(uint32_t tmem_c, uint32_t tmem_a, uint32_t bd_lo, uint32_t bd_hi, uint32_t idesc,
+                                             uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 d;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 d, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n"
+      "}\n" ::"r"(tmem_c), "r"(tmem_a), "r"(bd_lo), "r"(bd_hi), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 // fast transcendental forms for the tensor-core path (their ~1e-6 error is far below the operand rounding)
-__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// clock read that cannot be scheduled before `dep` is available (trace points inside arithmetic)
+__device__ __forceinline__ long long clock_after(float dep) {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(dep) : "memory");
+  return t;
+}
+__device__ __forceinline__ float fex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float frcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fsigmoid(float x) { return frcp(1.0f + fex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float ftanh(float x) { return 1.0f - 2.0f * frcp(fex2(2.8853900817779268f * x) + 1.0f); }
 
 // shared-memory matrix descriptors (sm_100 version bits).
 //   swizzled  : K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO); LBO unused
@@ -171,61 +218,104 @@ struct TcBwdParams {
 };
 
 // The slice lives in TMEM as the MMA's A operand (lane = row, one 32-bit column = two consecutive k).
-// forward: row r = gate*32 + unit (warp = gate, lane = unit), columns k/2 for k in [0, Kp)
-__device__ __forceinline__ void load_w_tmem_fwd(const float* __restrict__ w_hh, int H, int Kp, int u0, int warp, int lane) {
-  const int unit = u0 + lane;
-  const float* row = w_hh + ((size_t)warp * H + min(unit, H - 1)) * H;
+// forward: row r = gate*32 + unit (lane quadrant = gate, lane = unit), columns k/2 for k in [0, Kp).
+// Warp w loads gate w & 3, k-half w >> 2.  The global reads are coalesced (a quarter-warp reads 128 contiguous bytes
+// of one W_hh row), the 32 x 32 block is transposed through a padded shared-memory tile so that lane = row, and the
+// next block's loads are in flight while the current one is packed and stored.
+constexpr int WST = 36;                // padded row stride (floats) of the per-warp staging tile: conflict-free LDS.128
+__device__ __forceinline__ void load_w_tmem_fwd(const float* __restrict__ w_hh, int H, int Kp, int u0, int warp, int lane,
+                                                float* stage_all) {
+  const int q = warp & 3, hf = warp >> 2;
+  float* st = stage_all + (size_t)warp * 32 * WST;
   const bool vec = (H & 3) == 0;
-  for (int c = 0; c < Kp / 32; ++c) {
-    float f[32];
+  const int kbeg = hf * (Kp / 2), nblk = Kp / 64;                 // 32-wide k blocks of this warp's half
+  const int rr = lane >> 3, cc = (lane & 7) * 4;                  // this lane reads rows rr + 4 j, floats cc..cc+3
+  auto fetch = [&](int blk, float4 (&v)[8]) {
+    const int k = kbeg + blk * 32 + cc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = c * 32 + 4 * i;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8; ++j) {
+      const int unit = u0 + rr + 4 * j;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (unit < H) {
-        if (vec && k + 3 < H) q = __ldg(reinterpret_cast<const float4*>(row + k));
+        const float* row = w_hh + ((size_t)q * H + unit) * H;
+        if (vec && k + 3 < H) x = __ldg(reinterpret_cast<const float4*>(row + k));
         else {
-          if (k < H) q.x = __ldg(row + k);
-          if (k + 1 < H) q.y = __ldg(row + k + 1);
-          if (k + 2 < H) q.z = __ldg(row + k + 2);
-          if (k + 3 < H) q.w = __ldg(row + k + 3);
+          if (k < H) x.x = __ldg(row + k);
+          if (k + 1 < H) x.y = __ldg(row + k + 1);
+          if (k + 2 < H) x.z = __ldg(row + k + 2);
+          if (k + 3 < H) x.w = __ldg(row + k + 3);
         }
       }
-      f[4 * i] = q.x; f[4 * i + 1] = q.y; f[4 * i + 2] = q.z; f[4 * i + 3] = q.w;
+      v[j] = x;
     }
+  };
+  float4 cur[8], nxt[8];
+  fetch(0, cur);
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (blk + 1 < nblk) fetch(blk + 1, nxt);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(st + (rr + 4 * j) * WST + cc) = cur[j];
+    __syncwarp();
     uint32_t pk[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) pk[i] = pack_h2(f[2 * i], f[2 * i + 1]);
-    tmem_st_x16(((uint32_t)(32 * warp) << 16) + (uint32_t)(c * 16), pk);
+    for (int i = 0; i < 8; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(st + lane * WST + 4 * i);
+      pk[2 * i] = pack_h2(x.x, x.y);
+      pk[2 * i + 1] = pack_h2(x.z, x.w);
+    }
+    tmem_st_x16(((uint32_t)(32 * q) << 16) + (uint32_t)((kbeg + blk * 32) / 2), pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-// backward: A = W_slice^T: tile mt, row = unit 128 mt + 32 warp + lane, columns j/2 for this CTA's 128 gate rows j
+// backward: A = W_slice^T: tile mt, row = unit 128 mt + 32 q + lane, columns j/2 for this CTA's 128 gate rows j.
+// Lanes are consecutive units = consecutive addresses of one W_hh row: coalesced as is.  Warp w serves lane quadrant
+// w & 3 and the gates 2 (w >> 2), 2 (w >> 2) + 1; all 32 loads of a (tile, gate) block are issued before the first use.
 __device__ __forceinline__ void load_w_tmem_bwd(const float* __restrict__ w_hh, int H, int u0, int n_mt, int warp, int lane) {
+  const int q = warp & 3, hf = warp >> 2;
   for (int mt = 0; mt < n_mt; ++mt) {
-    const int u = 128 * mt + 32 * warp + lane;
-    for (int gate = 0; gate < 4; ++gate) {
+    const int u = 128 * mt + 32 * q + lane;
+#pragma unroll 1
+    for (int gi = 0; gi < 2; ++gi) {
+      const int gate = 2 * hf + gi;
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ul = u0 + i;
+        f[i] = (u < H && ul < H) ? __ldg(w_hh + ((size_t)gate * H + ul) * H + u) : 0.f;
+      }
       uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int ul0 = u0 + 2 * i, ul1 = ul0 + 1;
-        const float a = (u < H && ul0 < H) ? __ldg(w_hh + ((size_t)gate * H + ul0) * H + u) : 0.f;
-        const float b = (u < H && ul1 < H) ? __ldg(w_hh + ((size_t)gate * H + ul1) * H + u) : 0.f;
-        pk[i] = pack_h2(a, b);
-      }
-      tmem_st_x16(((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 64 + gate * 16), pk);
+      for (int i = 0; i < 16; ++i) pk[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+      tmem_st_x16(((uint32_t)(32 * q) << 16) + (uint32_t)(mt * 64 + gate * 16), pk);
     }
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+
+// forward MMA issue with a compile-time k extent: k-step j of block kb accumulates into chain j
+template <int NRG, int NKB>
+__device__ __forceinline__ void issue_fwd_mmas(uint32_t bd, uint32_t bd_hi, uint32_t idesc) {
+  constexpr uint32_t CHUNK = NRG * 128;
+  constexpr int NPc = 8 * NRG;
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      umma_f16_ts2(TMEM_D + j * NPc, (uint32_t)(kb * 32 + j * 8), bd + (uint32_t)(((kb * 8 + j * 2) * CHUNK) >> 4), bd_hi, idesc,
+                   kb > 0 ? 1u : 0u);
+}
 // ------------------------------------------------------------------------------------------------ forward
 // NRG = 8-row groups of batch columns per cluster (MMA N = 8 NRG): 1 when the group has <= 8 rows, else 2.
 // The bytes a CTA sends per step (C copies of 512 NRG B) are what bounds the hand-off (DSMEM ~20 B/clk/SM).
 template <int NRG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdParams P) {
   constexpr int NPc = 8 * NRG;                               // batch columns of the MMA
-  constexpr int RM = 2 * NRG;                                // cells per thread (rows warp + 4 r)
+  constexpr int RM = NRG;                                    // cells per thread (rows warp + 8 r)
+  constexpr int HN = NPc / 2;                                // accumulator columns one warp drains
   constexpr uint32_t CHUNK = NRG * 128;                      // one k-chunk (8 k) of the h tile: NRG core matrices
   constexpr uint32_t SLICE = 4 * CHUNK;                      // one CTA's h slice: 32 units = 4 k-chunks, contiguous
   extern __shared__ uint8_t smem_raw[];
@@ -238,8 +328,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   uint8_t* hstage = reinterpret_cast<uint8_t*>(gsm + 4 * NPc * 32);           // [2][SLICE]
   uint64_t* bars = reinterpret_cast<uint64_t*>(hstage + 2 * SLICE);           // [0] mma_done, [1..2] h_full[buf]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* wstage = reinterpret_cast<float*>(bars + 4);                         // [EW][32][WST] weight-load staging
   const uint32_t bt_addr = base;
-  const uint32_t hstage_addr = smem_u32(hstage);
   const uint32_t bar_mma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
   auto ht_off = [](int n, int k) -> uint32_t {               // byte offset of element (row n, k) in a tile / slice
     return (uint32_t)(k >> 3) * CHUNK + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
@@ -270,14 +360,13 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
     }
     *reinterpret_cast<uint4*>(Bt + (size_t)bufi * tile_bytes + ht_off(row, chunk * 8)) = *reinterpret_cast<uint4*>(hv);
   }
-  for (int e = tid; e < 2 * (int)SLICE / 16; e += blockDim.x) reinterpret_cast<uint4*>(hstage)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     mbar_init(bar_mma, 1);
     mbar_init(bar_full0, 1);
     mbar_init(bar_full0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == EW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -286,20 +375,20 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (*tmem_slot != 0u) __trap();                            // the whole TMEM was requested: the base must be column 0
-  if (warp < 4) {
-    load_w_tmem_fwd(D.w_hh, H, Kp, u0, warp, lane);
+  if (warp < EW) {
+    load_w_tmem_fwd(D.w_hh, H, Kp, u0, warp, lane, wstage);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
 
-  // cell ownership: thread (warp q < 4, lane) owns cells (n = q + 4 r, unit = lane), r < nr <= RM (nr is warp-uniform)
+  // cell ownership: thread (warp w < 8, lane) owns cells (n = w + 8 r, unit = lane), r < nr <= RM (nr is warp-uniform)
   float c[RM], h[RM], bias[RM][4];
   int len[RM];
   const int unit = u0 + lane;
-  const bool ulive = warp < 4 && unit < H;
-  const int nr = (warp < 4 && nn > warp) ? (nn - warp + 3) / 4 : 0;
+  const bool ulive = warp < EW && unit < H;
+  const int nr = (warp < EW && nn > warp) ? (nn - warp + 7) / 8 : 0;
 #pragma unroll
   for (int r = 0; r < RM; ++r) {
-    const int n = warp + 4 * r;
+    const int n = warp + 8 * r;
     len[r] = T; c[r] = 0.f; h[r] = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[r][g] = 0.f;
@@ -319,117 +408,147 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   const int ucl = min(unit, H - 1);                          // clamped: dead lanes read valid memory, results discarded
   // instruction descriptor: D f32, A/B fp16 K-major, N = NPc, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // un-swizzled K-major B descriptor: core matrices adjacent in K are CHUNK apart (LBO), 8-row groups 128 B apart (SBO)
+  const uint32_t bd_hi = (uint32_t)(128u >> 4) | (1u << 14);
+  const uint32_t bd_lo0 = ((bt_addr >> 4) & 0x3FFFu) | ((CHUNK >> 4) << 16);
   const bool leader = elect_one();
   cluster_sync_all();          // every CTA of the cluster is initialised (tiles, mbarriers) before any remote copy lands
   if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[9] = clock64();
 
+  const int q = warp & 3, hf = warp >> 2;
+  // this lane's two hand-off destinations (CTAs l & 7, (l & 7) + 8): their operand tiles and h_full barriers
+  uint32_t rtile[2], rbar[2];
+  bool dst_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int d = (lane & 7) + 8 * i;
+    dst_ok[i] = d < C;
+    rtile[i] = mapa(bt_addr, (uint32_t)min(d, C - 1));
+    rbar[i] = mapa(bar_full0, (uint32_t)min(d, C - 1));
+  }
+  float gxn[RM][4];
+  auto load_gx = [&](int tt) {
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      const int n = min(warp + 8 * r, nn - 1);
+      const float* gp = D.gx + ((size_t)tt * N + n0 + n) * 4 * H + ucl;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gxn[r][g] = (r < nr) ? __ldg(gp + (size_t)g * H) : 0.f;
+    }
+  };
+  if (warp < EW) load_gx(D.reverse ? T - 1 : 0);
   for (int s = 0; s < T; ++s) {
     const int t = D.reverse ? T - 1 - s : s;
     const int buf = s & 1;
     const bool tr = P.trace != nullptr && blockIdx.x == 0 && s == 5;
     if (tr && tid == 0) P.trace[0] = clock64();
-    if (warp == 4) {
-      // arm next step's hand-off barrier: C slices will land in the other tile
-      if (leader && s + 1 < T) mbar_arrive_expect_tx(bar_full0 + 8u * (uint32_t)(buf ^ 1), (uint32_t)C * SLICE);
-      if (s > 0) mbar_wait(bar_full0 + 8u * (uint32_t)buf, (uint32_t)(((s - 1) >> 1) & 1));   // h_{s-1} of all CTAs landed
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tr && lane == 0) P.trace[14] = clock64();
-      const uint32_t b0 = bt_addr + (uint32_t)buf * tile_bytes;
-      for (int kb = 0; kb < nkb; ++kb) {
+    if (warp == EW) {
+      if (leader) {
+        // arm next step's hand-off barrier: C slices will land in the other tile
+        if (s + 1 < T) mbar_arrive_expect_tx(bar_full0 + 8u * (uint32_t)(buf ^ 1), (uint32_t)(C * nn) * 64u);
+        if (s > 0) mbar_wait(bar_full0 + 8u * (uint32_t)buf, (uint32_t)(((s - 1) >> 1) & 1));   // h_{s-1} of all CTAs landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the peers' st.async data -> the MMA's operand reads
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tr) P.trace[14] = clock64();
+        // k-step j of block kb accumulates into chain j: four independent accumulator chains, 2 k-chunks per k-step
+        const uint32_t bd = bd_lo0 + (uint32_t)buf * (tile_bytes >> 4);
+        if (nkb == 8) issue_fwd_mmas<NRG, 8>(bd, bd_hi, idesc);          // H in (448, 512]: every offset an immediate
+        else if (nkb == 4) issue_fwd_mmas<NRG, 4>(bd, bd_hi, idesc);     // H in (192, 256]
+        else {
+          uint32_t a = 0, b = bd;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                       // k-step j of block kb accumulates into chain j
-          // un-swizzled K-major: core matrices adjacent in K are CHUNK apart (LBO), 8-row groups 128 B apart (SBO)
-          const uint64_t bd = make_desc_none(b0 + (uint32_t)(kb * 8 + j * 2) * CHUNK, CHUNK, 128u);
-          if (leader) umma_f16_ts(TMEM_D + j * NPc, (uint32_t)(kb * 32 + j * 8), bd, idesc, kb > 0 ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) umma_f16_ts2(TMEM_D + j * NPc, a + j * 8, b + j * ((2 * CHUNK) >> 4), bd_hi, idesc, 0u);
+          for (int kb = 1; kb < nkb; ++kb) {
+            a += 32; b += (8 * CHUNK) >> 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_f16_ts2(TMEM_D + j * NPc, a + j * 8, b + j * ((2 * CHUNK) >> 4), bd_hi, idesc, 1u);
+          }
         }
+        umma_commit(bar_mma);
+        if (tr) P.trace[1] = clock64();
       }
-      if (leader) umma_commit(bar_mma);
-      if (tr && lane == 0) P.trace[1] = clock64();
       __syncwarp();
     } else {
-      // input-projection terms of this step (independent of the recurrence: issued before the wait)
+      // input-projection terms: this step's were loaded during the previous step (gxn), the next step's loads are
+      // issued now and complete under this step's MMAs / cell update
       float gx[RM][4];
 #pragma unroll
-      for (int r = 0; r < RM; ++r) {
-        const int n = min(warp + 4 * r, nn - 1);
-        const float* gp = D.gx + ((size_t)t * N + n0 + n) * 4 * H + ucl;
+      for (int r = 0; r < RM; ++r)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) gx[r][g] = (r < nr) ? __ldg(gp + (size_t)g * H) + bias[r][g] : 0.f;
-      }
+        for (int g = 0; g < 4; ++g) gx[r][g] = gxn[r][g] + bias[r][g];
+      if (s + 1 < T) load_gx(D.reverse ? T - 2 - s : s + 1);
       if (tr && tid == 0) P.trace[2] = clock64();
       mbar_wait(bar_mma, (uint32_t)(s & 1));
       if (tr && tid == 0) P.trace[3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float acc[NPc];
       {
-        uint32_t v[32];                                     // 4 chains x NPc columns
-        tmem_ld_x32(TMEM_D + ((uint32_t)(32 * warp) << 16), v);
-        if (NRG == 2) {
+        // gate q of batch columns [hf HN, hf HN + HN): the four chains' partial sums
+        uint32_t v[4][HN];
+        const uint32_t ta = TMEM_D + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * HN);
 #pragma unroll
-          for (int n = 0; n < NPc; ++n) acc[n] = __uint_as_float(v[n]) + __uint_as_float(v[NPc + n]);
-          tmem_ld_x32(TMEM_D + ((uint32_t)(32 * warp) << 16) + 2 * NPc, v);
-#pragma unroll
-          for (int n = 0; n < NPc; ++n) acc[n] += __uint_as_float(v[n]) + __uint_as_float(v[NPc + n]);
-        } else {
-#pragma unroll
-          for (int n = 0; n < NPc; ++n)
-            acc[n] = (__uint_as_float(v[n]) + __uint_as_float(v[8 + n])) + (__uint_as_float(v[16 + n]) + __uint_as_float(v[24 + n]));
+        for (int j = 0; j < 4; ++j) {
+          if (NRG == 1) tmem_ld_x4_nowait(ta + j * NPc, v[j]); else tmem_ld_x8_nowait(ta + j * NPc, v[j]);
         }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // accumulator reads precede the next step's MMAs
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // accumulator reads precede the next step's MMAs
 #pragma unroll
-      for (int n = 0; n < NPc; ++n) gsm[(warp * NPc + n) * 32 + lane] = acc[n];   // gate `warp`, unit `lane`
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int n = 0; n < HN; ++n)
+          gsm[(q * NPc + hf * HN + n) * 32 + lane] =
+              (__uint_as_float(v[0][n]) + __uint_as_float(v[1][n])) + (__uint_as_float(v[2][n]) + __uint_as_float(v[3][n]));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tr && tid == 0) P.trace[4] = clock64();
-      uint8_t* hs = hstage + (size_t)buf * SLICE;
       float av[RM][4], hout[RM];                             // activated gates / masked output, stored after the hand-off
-      // straight-line (branch-free) cell updates so the RM independent dependency chains interleave
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {                                        // warp-uniform
-          const int n = warp + 4 * r;
+          const int n = warp + 8 * r;
           const float Gi = gsm[(0 * NPc + n) * 32 + lane] + gx[r][0];
           const float Gf = gsm[(1 * NPc + n) * 32 + lane] + gx[r][1];
           const float Gg = gsm[(2 * NPc + n) * 32 + lane] + gx[r][2];
           const float Go = gsm[(3 * NPc + n) * 32 + lane] + gx[r][3];
+          if (tr && tid == 0 && r == 0) P.trace[16] = clock_after(Gi + Gf + Gg + Go);
           av[r][0] = fsigmoid(Gi); av[r][1] = fsigmoid(Gf); av[r][2] = ftanh(Gg); av[r][3] = fsigmoid(Go);
         }
       }
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {
-          const int n = warp + 4 * r;
+          const int n = warp + 8 * r;
           const float cn = av[r][1] * c[r] + av[r][0] * av[r][2];
           const float hn = av[r][3] * ftanh(cn);
           const bool m = t < len[r];
           c[r] = m ? cn : c[r];
           h[r] = m ? hn : h[r];
           hout[r] = m ? hn : 0.f;
-          *reinterpret_cast<__half*>(hs + ht_off(n, lane)) = __float2half_rn(ulive ? h[r] : 0.f);
+          if (tr && tid == 0 && r == 0) P.trace[17] = clock_after(hn);
+          if (s + 1 < T) {
+            // Hand-off: the 8 lanes that hold one 16-byte chunk (8 consecutive units of row n, fp16) assemble it with
+            // shuffles, then lane l stores it straight into the OTHER operand tile of CTAs l & 7 and (l & 7) + 8
+            // (st.async: the store completes on the destination's h_full barrier; own CTA included).  Reuse is safe
+            // without further synchronisation: a destination's tile (buf^1) was last read by its MMAs of step s-1,
+            // which completed before that CTA produced the h_{s-1} values this CTA had to receive before computing h_s.
+            const uint32_t hb = (uint32_t)__half_as_ushort(__float2half_rn(ulive ? h[r] : 0.f));
+            const uint32_t pb = __shfl_xor_sync(0xffffffffu, hb, 1);
+            const uint32_t w = (lane & 1) ? (pb | (hb << 16)) : (hb | (pb << 16));
+            const int gb = lane & ~7;
+            const uint32_t w0 = __shfl_sync(0xffffffffu, w, gb), w1 = __shfl_sync(0xffffffffu, w, gb + 2);
+            const uint32_t w2 = __shfl_sync(0xffffffffu, w, gb + 4), w3 = __shfl_sync(0xffffffffu, w, gb + 6);
+            const uint32_t off = (uint32_t)(buf ^ 1) * tile_bytes + (uint32_t)(crank * 4 + (lane >> 3)) * CHUNK +
+                                 (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u;
+            const uint32_t boff = 8u * (uint32_t)(buf ^ 1);
+            if (tr && tid == 0 && r == 0) P.trace[18] = clock_after(__uint_as_float(w0 ^ w1 ^ w2 ^ w3));
+            if (dst_ok[0]) st_async_v4(rtile[0] + off, w0, w1, w2, w3, rbar[0] + boff);
+            if (dst_ok[1]) st_async_v4(rtile[1] + off, w0, w1, w2, w3, rbar[1] + boff);
+          }
         }
       }
       if (tr && tid == 0) P.trace[13] = clock64();
-      if (s + 1 < T) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // staged slice -> visible to the bulk-copy engine
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tr && tid == 0) P.trace[5] = clock64();
-        // One copy per destination CTA (own CTA included) into the OTHER operand tile, completing on the
-        // destination's h_full barrier.  Reuse is safe without further synchronisation: a destination's tile
-        // (buf^1) was last read by its MMAs of step s-1, which completed before that CTA produced the h_{s-1}
-        // slice this CTA had to receive before computing h_s; hstage[buf] is rewritten at step s+2, after this
-        // CTA received every h_{s+1} slice, each produced after the producer consumed this copy.
-        const int dstc = (lane < 4) ? warp * 4 + lane : 99;  // 4 copies per warp
-        if (dstc < C) {
-          const uint32_t dst = mapa(bt_addr + (uint32_t)(buf ^ 1) * tile_bytes + (uint32_t)crank * SLICE, (uint32_t)dstc);
-          const uint32_t bar = mapa(bar_full0 + 8u * (uint32_t)(buf ^ 1), (uint32_t)dstc);
-          bulk_copy_to_cluster(dst, hstage_addr + (uint32_t)buf * SLICE, SLICE, bar);
-        }
-      }
       if (tr && tid == 0) P.trace[6] = clock64();
       // outputs and the tensors saved for backward leave after the hand-off: off the recurrence's critical path
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
-        const int n = warp + 4 * r;
+        const int n = warp + 8 * r;
         if (ulive && r < nr) {
           const size_t row = (size_t)t * N + n0 + n;
           D.out[row * D.out_ld + unit] = hout[r];
@@ -444,10 +563,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
     if (tr && tid == 0) P.trace[7] = clock64();
   }
   if (P.trace && blockIdx.x == 0 && tid == 0) { P.trace[10] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.trace[12] = (long long)g; }
-  if (warp < 4) {
+  if (warp < EW) {
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
-      const int n = warp + 4 * r;
+      const int n = warp + 8 * r;
       if (ulive && r < nr) {
         if (D.hT) D.hT[(size_t)(n0 + n) * H + unit] = h[r];
         if (D.cT) D.cT[(size_t)(n0 + n) * H + unit] = c[r];
@@ -456,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(TMEM_COLS));
+  if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(TMEM_COLS));
   cluster_sync_all();          // no CTA exits while a peer could still address its shared memory
 }
 
@@ -464,7 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
 template <int NRG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdParams P) {
   constexpr int NPc = 8 * NRG;
-  constexpr int RM = 2 * NRG;
+  constexpr int RM = NRG;
   constexpr int KB_BYTES = 2 * NPc * 128;                    // one k-block (64 gate rows) of the dG tile: hi rows | lo rows
   constexpr int PART = NPc * 32 * 4;                         // one (source, owner) block of dh partials
   extern __shared__ uint8_t smem_raw[];
@@ -498,7 +617,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
     mbar_init(bar_recv0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == EW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -508,7 +627,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (*tmem_slot != 0u) __trap();
   const int n_mt = (P.C * UC + 127) / 128;                  // 128-unit output tiles that hold real units
-  if (warp < 4) {
+  if (warp < EW) {
     load_w_tmem_bwd(D.w_hh, H, u0, n_mt, warp, lane);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -516,12 +635,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   float dc[RM], dhr[RM];
   int len[RM];
   const int unit = u0 + lane;
-  const bool ulive = warp < 4 && unit < H;
+  const bool ulive = warp < EW && unit < H;
   const int ucl = min(unit, H - 1);
-  const int nr = (warp < 4 && nn > warp) ? (nn - warp + 3) / 4 : 0;
+  const int nr = (warp < EW && nn > warp) ? (nn - warp + 7) / 8 : 0;
 #pragma unroll
   for (int r = 0; r < RM; ++r) {
-    const int n = warp + 4 * r;
+    const int n = warp + 8 * r;
     len[r] = T; dc[r] = 0.f; dhr[r] = 0.f;
     if (ulive && n < nn) {
       const int gn = n0 + n;
@@ -532,6 +651,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   }
   // D f32, A fp16 from TMEM (W_slice^T), B fp16 K-major, N = 2 NPc (hi | lo), M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)((2 * NPc) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // 128-byte-swizzled K-major B descriptor (8-row groups 1024 B apart), as make_desc_sw128
+  const uint32_t bd_hi = (uint32_t)(1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t bd_lo0 = ((base >> 4) & 0x3FFFu) | (1u << 16);
   const bool leader = elect_one();
   cluster_sync_all();
   if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[9] = clock64();
@@ -548,7 +670,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
       if (r < nr) {
-        const int gn = n0 + warp + 4 * r;
+        const int gn = n0 + warp + 8 * r;
         const size_t row = (size_t)tq * N + gn;
         const float* gp = D.gates + row * 4 * H + ucl;
         pf[r][0] = __ldg(gp); pf[r][1] = __ldg(gp + (size_t)H); pf[r][2] = __ldg(gp + (size_t)2 * H); pf[r][3] = __ldg(gp + (size_t)3 * H);
@@ -573,7 +695,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       }
     }
   };
-  if (warp < 4) { load_raw(0); derive(); }
+  if (warp < EW) { load_raw(0); derive(); }
+  const int q = warp & 3, hf = warp >> 2;
 
   for (int s = 0; s < T; ++s) {
     const int t = D.reverse ? s : T - 1 - s;
@@ -582,12 +705,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
     const bool tr = P.trace != nullptr && blockIdx.x == 0 && s == 5;
     if (tr && tid == 0) P.trace[0] = clock64();
     float dGs[RM][4];
-    if (warp < 4) {
+    if (warp < EW) {
       // ---- elementwise BPTT of this CTA's cells -> dG_t as fp16 hi/lo operand rows n / NPc+n
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {
-          const int n = warp + 4 * r;
+          const int n = warp + 8 * r;
           const bool m = ulive && t < len[r];
           const float dh = dhr[r] + pf[r][6];
           const float dct = dc[r] + dh * pf[r][0];
@@ -616,25 +739,26 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
     const bool stop = last && D.dh0 == nullptr;             // the last dh_prev only feeds dh0
     if (!stop) __syncthreads();
     if (tr && tid == 0) P.trace[1] = clock64();
-    if (warp == 4) {
+    if (warp == EW) {
       if (stop) break;
-      if (leader) mbar_arrive_expect_tx(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)C * part_bytes);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int mt = 0; mt < n_mt; ++mt) {
+      if (leader) {
+        mbar_arrive_expect_tx(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)C * part_bytes);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int mt = 0; mt < n_mt; ++mt) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                    // K = 128 gate rows = 8 steps of 16
-          const uint64_t bd = make_desc_sw128(base + (uint32_t)(ks >> 2) * KB_BYTES + (uint32_t)(ks & 3) * 32u);
-          if (leader) umma_f16_ts(TMEM_D + mt * 32, (uint32_t)(mt * 64 + ks * 8), bd, idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)                    // K = 128 gate rows = 8 steps of 16
+            umma_f16_ts2(TMEM_D + mt * 32, (uint32_t)(mt * 64 + ks * 8),
+                         bd_lo0 + (uint32_t)(((ks >> 2) * KB_BYTES + (ks & 3) * 32) >> 4), bd_hi, idesc, ks > 0 ? 1u : 0u);
         }
+        umma_commit(bar_mma);
       }
-      if (leader) umma_commit(bar_mma);
       __syncwarp();
     } else {
       // dG_t leaves for global memory (it is d gx, consumed by the batched weight / input gradient GEMMs)
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         if (ulive && r < nr) {
-          float* dg = D.dgates + ((size_t)t * N + n0 + warp + 4 * r) * 4 * H + unit;
+          float* dg = D.dgates + ((size_t)t * N + n0 + warp + 8 * r) * 4 * H + unit;
           dg[0] = dGs[r][0]; dg[(size_t)H] = dGs[r][1]; dg[(size_t)2 * H] = dGs[r][2]; dg[(size_t)3 * H] = dGs[r][3];
         }
       }
@@ -643,36 +767,39 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       mbar_wait(bar_mma, (uint32_t)(s & 1));
       if (tr && tid == 0) P.trace[2] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // partial dh[unit = 128 mt + 32 warp + lane, n] -> staged per owner CTA 4 mt + warp as [n][lane]
+      // partial dh[unit = 128 mt + 32 q + lane, n] -> staged per owner CTA 4 mt + q as [n][lane]; warp w drains the
+      // tiles mt = hf, hf + 2 of its lane quadrant
       float* st = stage + (size_t)buf * 16 * NPc * 32;
-      for (int mt = 0; mt < n_mt; ++mt) {
-        const int owner = 4 * mt + warp;
-        if (NRG == 2) {
-          uint32_t v[32];
-          tmem_ld_x32(TMEM_D + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 32), v);
-          if (owner < C) {
+      {
+        uint32_t v[2][2 * NPc];
 #pragma unroll
-            for (int n = 0; n < NPc; ++n)
-              st[(owner * NPc + n) * 32 + lane] = (__uint_as_float(v[n]) + __uint_as_float(v[NPc + n])) * (1.0f / DG_SCALE);
+        for (int i = 0; i < 2; ++i) {
+          const int mt = hf + 2 * i;
+          if (mt < n_mt) {
+            const uint32_t ta = TMEM_D + ((uint32_t)(32 * q) << 16) + (uint32_t)(mt * 32);
+            if (NRG == 1) tmem_ld_x16_nowait(ta, v[i]);
+            else { tmem_ld_x16_nowait(ta, v[i]); tmem_ld_x16_nowait(ta + 16, v[i] + 16); }
           }
-        } else {
-          uint32_t v[16];
-          tmem_ld_x16(TMEM_D + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mt * 32), v);
-          if (owner < C) {
+        }
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int mt = hf + 2 * i, owner = 4 * mt + q;
+          if (mt < n_mt && owner < C) {
 #pragma unroll
             for (int n = 0; n < NPc; ++n)
-              st[(owner * NPc + n) * 32 + lane] = (__uint_as_float(v[n]) + __uint_as_float(v[NPc + n])) * (1.0f / DG_SCALE);
+              st[(owner * NPc + n) * 32 + lane] = (__uint_as_float(v[i][n]) + __uint_as_float(v[i][NPc + n])) * (1.0f / DG_SCALE);
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tr && tid == 0) P.trace[3] = clock64();
       // reduce-scatter: one block of nn rows per owner, into the owner's recv[buf][src = this CTA], completing on
       // the owner's recv_full[buf].  stage[buf] / recv[buf] are reused at step s+2: by then this CTA has consumed
       // every owner's step-(s+1) block, each sent after that owner consumed this step's copies.
-      const int dstc = (lane < 4) ? warp * 4 + lane : 99;
+      const int dstc = (lane < 2) ? warp * 2 + lane : 99;
       if (dstc < C) {
         const uint32_t dst = mapa(recv_addr + (uint32_t)((buf * 16 + crank) * PART), (uint32_t)dstc);
         const uint32_t bar = mapa(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)dstc);
@@ -686,7 +813,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {
-          const int n = warp + 4 * r;
+          const int n = warp + 8 * r;
           float s0 = dhr[r], s1 = 0.f, s2 = 0.f, s3 = 0.f;  // dhr: non-zero only for frozen (masked) cells
           for (int src = 0; src + 3 < C; src += 4) {
             s0 += rb[((src + 0) * NPc + n) * 32 + lane];
@@ -702,10 +829,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
     if (tr && tid == 0) P.trace[5] = clock64();
   }
   if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[10] = clock64();
-  if (warp < 4) {
+  if (warp < EW) {
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
-      const int n = warp + 4 * r;
+      const int n = warp + 8 * r;
       if (ulive && r < nr) {
         if (D.dh0) D.dh0[(size_t)(n0 + n) * H + unit] = dhr[r];
         if (D.dc0) D.dc0[(size_t)(n0 + n) * H + unit] = dc[r];
@@ -714,7 +841,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(TMEM_COLS));
+  if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(TMEM_COLS));
   cluster_sync_all();
 }
 
@@ -722,7 +849,8 @@ struct TcPlan { int C, G, Ng, Kp, nrg; };
 int g_cluster_budget = 0;     // 0 = all co-resident clusters; > 0: cap (two recurrences sharing the GPU on two streams)
 
 size_t fwd_smem(int Kp, int nrg) {
-  return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64;
+  return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64 +
+         (size_t)EW * 32 * WST * 4;
 }
 size_t bwd_smem(int nrg) { return 1024 + (size_t)2 * 2 * 8 * nrg * 128 + (size_t)4 * 16 * 8 * nrg * 32 * 4 + 64; }
 
@@ -819,8 +947,9 @@ int launch_fwd(TcFwdParams& P, const TcPlan& p, int ndir, int maxc, cudaStream_t
   P.trace = trace_buf();
   rc = cluster_launch(lstm_tc_fwd_kernel<NRG>, P, ndir * p.G * p.C, p.C, smem, s, "lstm_tc_fwd_kernel");
   cudaStreamSynchronize(s);
-  long long h[16];
-  cudaMemcpy(h, P.trace, 128, cudaMemcpyDeviceToHost);
+  long long h[24];
+  cudaMemcpy(h, P.trace, 192, cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[lstm fwd trace] cells: gates_read %lld h_ready %lld chunk_packed %lld\n", h[16] - h[0], h[17] - h[0], h[18] - h[0]);
   fprintf(stderr, "[lstm fwd trace] T=%d C=%d G=%d Ng=%d nrg=%d max_clusters=%d setup %lld cyc, loop %lld cyc (%lld per step), block0 wall %lld ns\n",
           P.T, p.C, p.G, p.Ng, NRG, maxc, h[9] - h[8], h[10] - h[9], (h[10] - h[9]) / P.T, h[12] - h[11]);
   fprintf(stderr, "[lstm fwd trace] step5: mma warp h_full %lld issued %lld | epi: gx_loaded %lld mma_done %lld gates_xchg %lld cells %lld fence+bar %lld copies_issued %lld end %lld\n",
