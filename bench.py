@@ -174,7 +174,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     import variational_mmt_b200 as vm
-    from variational_mmt_b200 import synthetic, _lib
+    from variational_mmt_b200 import synthetic, _lib, ops
 
     mk, bk, desc = WORKLOADS[args.workload]
     B = bk["batch_size"]
@@ -347,7 +347,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": desc, "global_batch": B * n_gpus,
                        "tokens_per_step": tok / args.steps, "params": n_params,
-                       "gemm": "tf32 tcgen05 (fp32 storage, fp32 accumulate)" if _lib.lib.vmmt_get_gemm_mode() == 0
+                       "gemm": "tf32 tcgen05 (fp32 storage, fp32 accumulate)" if ops.get_gemm_mode() == 0
                                else "fp32 simt",
                        "parallelism": "dp%d" % n_gpus,
                        "exchange": optim.exchange_in_use,
@@ -425,7 +425,7 @@ def run_decode(args):
     if world > 1:
         dist.barrier()
     import variational_mmt_b200 as vm
-    from variational_mmt_b200 import synthetic, _lib
+    from variational_mmt_b200 import synthetic, _lib, ops
     opt = synthetic.make_opt(emb=mk["emb"], hidden=mk["hidden"], z_dim=mk["z"], conditional=True, dropout=0.5)
     fields = synthetic.make_fields(mk["v"], mk["v"])
     torch.manual_seed(3435)
@@ -546,7 +546,7 @@ def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
 
     def run():
         _lib.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), 1, M, H, V, fptr(lse),
-                  fptr(stats), fptr(ws), wsb, stream())
+                  fptr(stats), fptr(ws), wsb, 0, stream())
     for _ in range(3):
         run()
     times = []

@@ -30,12 +30,15 @@ const char* vmmt_last_error(void);
 int vmmt_version(void);
 /* number of kernels libvmmt has launched in this process (bench.py's gpu_launches). */
 unsigned long long vmmt_launch_count(void);
-/* 0 = auto (tcgen05 TF32 tensor-core GEMM where eligible), 1 = exact-fp32 SIMT GEMM everywhere. */
-void vmmt_set_gemm_mode(int mode);
-int vmmt_get_gemm_mode(void);
-/* 1: the GEMMs launched next are background work (weight gradients on a low-priority side stream): one tile per CTA
- * instead of the persistent per-SM tile loop, so that SMs free up for critical-path kernels between tiles.  Host flag. */
-void vmmt_gemm_set_background(int on);
+
+/* Per-call arithmetic / scheduling flags (`flags` arguments below).  The library keeps NO process-global mode: the only
+ * state it holds are per-device caches (function attributes, SM counts) behind a mutex. */
+#define VMMT_F_EXACT 1       /* exact-fp32 SIMT contractions / recurrences instead of tensor cores (parity debugging) */
+#define VMMT_F_BF16 2        /* tensor-core contractions on bf16 operands (fp32 accumulate) instead of TF32 */
+#define VMMT_F_BACKGROUND 4  /* optimiser-only work (weight gradients on a low-priority side stream): one tile per CTA instead
+                                of the persistent per-SM tile loop, so that SMs free up for critical-path kernels between tiles */
+#define VMMT_F_NO_SPLITK 8   /* one accumulation chain per output element in fixed K order: run-to-run deterministic and
+                                batch-invariant (a row's result does not depend on how many rows the call has) */
 
 /* C[M,N] (ldc) = act(op(A) op(B) + bias[N]) (+C if accumulate).
  * a_kmajor: A stored [M,K] (1) or [K,M] (0);  b_kmajor: B stored [N,K] (1, nn.Linear weight) or [K,N] (0).
@@ -43,7 +46,7 @@ void vmmt_gemm_set_background(int on);
  * NormalVariationalEncoder.py:18-25,35-43; the input projections inside nn.LSTM (Models.py:124-129). */
 int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
               float* C, int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
-              void* stream);
+              int flags, void* stream);
 
 /* C[M,N] = act(A1 B1^T + A2 B2^T + bias): two operand pairs ([rows,K] row-major, the nn.Linear layout) contracted into one
  * accumulator in one launch.  Replaces the pairs of nn.Linear-on-a-concatenation the reference spells with torch.cat:
@@ -51,7 +54,7 @@ int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t
  * (GlobalAttention.py:187-190). */
 int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, int64_t ldb1, int K1, const float* A2, int64_t lda2,
                    const float* B2, int64_t ldb2, int K2, float* C, int64_t ldc, int M, int N, const float* bias, int act,
-                   void* stream);
+                   int flags, void* stream);
 
 /* Embedding gather / dense scatter-add (Embeddings.py:169-188; nn.Embedding padding_idx row gets no grad). */
 int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int E, float* out, void* stream);
@@ -95,14 +98,13 @@ typedef struct VmmtLstmDirBwd {
 } VmmtLstmDirBwd;
 
 size_t vmmt_lstm_workspace_bytes(int ndir, int N, int H);
-/* Cap on the thread-block clusters the next recurrence launches may occupy (0 = as many as are co-resident).  Two
- * independent recurrences issued on two streams (source encoder / target encoder) share the GPU with it. */
-void vmmt_lstm_set_cluster_budget(int max_clusters);
 int vmmt_lstm_seq_supported(int ndir, int N, int H);
-int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
-                      void* workspace, size_t workspace_bytes, void* stream);
-int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H,
-                      void* workspace, size_t workspace_bytes, void* stream);
+/* cluster_budget: cap on the thread-block clusters this launch may occupy (0 = as many as are co-resident).  Two
+ * independent recurrences issued on two streams (source encoder / target encoder) share the GPU with it. */
+int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int flags,
+                      int cluster_budget, void* workspace, size_t workspace_bytes, void* stream);
+int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int flags,
+                      int cluster_budget, void* workspace, size_t workspace_bytes, void* stream);
 /* single-step cell on pre-summed gate pre-activations (decode with large sentences x beam). */
 int vmmt_lstm_cell_fwd(const float* gates_pre, const float* b_ih, const float* b_hh, const float* rowbias,
                        const float* c_prev, float* h_out, float* c_out, int N, int H, void* stream);
@@ -141,6 +143,39 @@ int vmmt_kl_bwd(const float* mu_q, const float* sd_q, const float* mu_p, const f
                 float* dsd_q, float* dmu_p /*or NULL*/, float* dsd_p /*or NULL*/,
                 const float* gscale /*device scalar or NULL*/, float scale, int B, int Z, void* stream);
 
+/* ---- batch-row linear layers in exact fp32 (csrc/rowlin.cu): the location / scale MLPs of the prior, posterior and
+ * image networks (NormalVariationalEncoder.py:12-43,93-110,164-228,286-304) have M = batch rows against K up to 3048:
+ * weight-bandwidth bound, cluster split-K (deterministic), the same arithmetic per row whatever M is.
+ *   w_transposed = 0: out_p[M,N] = act_p(x_p[M,K] W_p[N,K]^T + b_p)
+ *   w_transposed = 1: out_p[M,N] = x_p[M,K] W_p[K,N]  with x_p := x_p * act'(y_p) applied on load (input gradient of a
+ *                     layer whose activation output is y_p); xt_out, if set, receives that transformed x
+ * x_p is the column-wise concatenation of nseg <= 3 matrices (segment i holds logical columns [k0_i, k0_{i+1})).
+ * nprob = 2: two independent problems, or (sum_outputs) both accumulated into problem 0's output. */
+typedef struct VmmtRowLinSeg {
+  const float* p;
+  int64_t ld;
+  int32_t k0;
+  int32_t pad_;
+} VmmtRowLinSeg;
+typedef struct VmmtRowLin {
+  VmmtRowLinSeg seg[3];
+  int32_t nseg;
+  int32_t act;           /* activation of the output (forward form) */
+  const float* y;        /* gradient form: activation output whose derivative scales x on load, or NULL */
+  int64_t ldy;
+  int32_t yact;
+  int32_t pad_;
+  const float* w;
+  int64_t ldw;
+  const float* bias;     /* [N] or NULL */
+  float* out;
+  int64_t ldo;
+  float* xt_out;         /* [M,K] or NULL */
+  int64_t ld_xt;
+} VmmtRowLin;
+int vmmt_rowlin(const VmmtRowLin* probs, int nprob, int sum_outputs, int w_transposed, int M, int N, int K,
+                void* stream);
+
 /* ---- image-feature head (NormalVariationalEncoder.py:286-299) and its loss (VILoss.py:22-56,317-332) */
 int vmmt_gate_fwd(const float* z, const float* w, const float* bias, float* gate /*[B]*/, float* gated,
                   int B, int Z, void* stream);
@@ -157,27 +192,27 @@ size_t vmmt_generator_workspace_bytes(int M, int V);
 int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b, const int64_t* target,
                            int64_t pad_idx, int M, int H, int V, float* lse /*[M]*/,
                            float* stats3 /*{nll_sum, n_words, n_correct}*/, void* workspace,
-                           size_t workspace_bytes, void* stream);
+                           size_t workspace_bytes, int flags, void* stream);
 int vmmt_generator_nll_bwd(const float* x, const float* W, const float* b, const int64_t* target,
                            int64_t pad_idx, const float* lse, const float* gscale /*device scalar or NULL*/,
                            float scale, int M, int H, int V,
                            float* dx /*or NULL*/, float* dW /*accumulated, or NULL*/, float* db /*accumulated, or NULL*/,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, int flags, void* stream);
 /* dW += dlogits^T x, db += colsum(dlogits) from the dlogits vmmt_generator_nll_bwd left in `workspace` (when it was
  * called with dW = db = NULL): lets the host issue the weight gradient on another stream. */
 int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW, float* db,
-                             void* stream);
+                             int flags, void* stream);
 int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H, int V,
-                            float* out /*[M,V]*/, float* lse_ws /*[M]*/, void* stream);
+                            float* out /*[M,V]*/, float* lse_ws /*[M]*/, int flags, void* stream);
 
 /* Beam-search form of the generator (TranslatorMultimodalVI.py:199 `self.model.generator.forward(dec_out)` followed by
  * Beam.advance's topk over beam x vocabulary, Beam.py:64-104): the GEMM epilogue keeps, per row and 128-column tile,
  * {max, sum exp} and the tile's K best logits; the [M,V] log-prob matrix is never written.  Requires the tensor-core
  * GEMM (vmmt_generator_topk_supported); otherwise use vmmt_generator_logprobs + vmmt_beam_advance. */
 size_t vmmt_generator_topk_workspace_bytes(int M, int V, int K);
-int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V);
+int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V, int flags);
 int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, int H, int V, int K, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        size_t workspace_bytes, int flags, void* stream);
 
 /* ---- optimiser: global-norm clip + Adam on flat buffers (Optim.py:69-70,94-96) */
 /* model.zero_grad() (TrainerMultimodal.py:627-628) on the flat gradient buffer with at most max_blocks resident blocks

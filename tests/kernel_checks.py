@@ -307,5 +307,57 @@ def check_optim(tol=1e-5):
     return out
 
 
+def check_rowmlp(tol=1e-5):
+    """ops.row_mlp (csrc/rowlin.cu, exact fp32, cluster split-K) against fp64 torch: the prior / posterior / image-head
+    shapes of config 1, a segmented input with gradients to a subset of the segments, ragged dims, M > one row block."""
+    from variational_mmt_b200 import ops
+    out = []
+    exact = 5e-7          # fp32 FMA chains of <= 3048 terms: far below TF32's 1e-3 in either GEMM mode
+    cases = [("posterior", 40, [500, 500, 2048], 500, 500, 2, [False, True, False]),
+             ("prior", 40, [500], 500, 500, 2, [True]),
+             ("image-head", 40, [500], 2048, 2048, 1, [True]),
+             ("ragged", 7, [33, 50, 21], 45, 19, 2, [True, False, True]),
+             ("tiny", 5, [64], 24, 24, 2, [False]),
+             ("many-rows", 250, [500], 500, 500, 2, [False])]
+    for name, M, ks, N1, N2, nh, need in cases:
+        K = sum(ks)
+        xs = [(_r(M, k, scale=0.5, seed=100 + i)).requires_grad_(nd) for i, (k, nd) in enumerate(zip(ks, need))]
+        heads = []
+        for hd in range(nh):
+            heads.append([torch.nn.Parameter(_r(N1, K, scale=0.05, seed=110 + hd)), torch.nn.Parameter(_r(N1, scale=0.1, seed=112 + hd)),
+                          torch.nn.Parameter(_r(N2, N1, scale=0.05, seed=114 + hd)), torch.nn.Parameter(_r(N2, scale=0.1, seed=116 + hd))])
+        acts = (ops.ACT_NONE, ops.ACT_SOFTPLUS)[:nh]
+        ys = ops.row_mlp(xs, heads, acts)
+        wy = [_r(M, N2, seed=120 + hd) for hd in range(nh)]
+        sum((y * w).sum() for y, w in zip(ys, wy)).backward()
+        ops.join_side()
+        torch.cuda.synchronize()
+        xr = [x.detach().double().requires_grad_(nd) for x, nd in zip(xs, need)]
+        hr = [[t.detach().double().requires_grad_(True) for t in hd] for hd in heads]
+        xc = torch.cat(xr, 1)
+        yr = []
+        for hd, (W1, b1, W2, b2) in enumerate(hr):
+            y = F.relu(xc @ W1.t() + b1) @ W2.t() + b2
+            yr.append(F.softplus(y) if hd == 1 else y)
+        sum((y * w.double()).sum() for y, w in zip(yr, wy)).backward()
+        for hd in range(nh):
+            out.append((f"rowmlp {name} y{hd}", _rel(ys[hd], yr[hd]), exact))
+            for j, nm in enumerate(("dW1", "db1", "dW2", "db2")):
+                out.append((f"rowmlp {name} head{hd} {nm}", _rel(heads[hd][j].grad, hr[hd][j].grad), tol))
+        for i, nd in enumerate(need):
+            if nd:
+                out.append((f"rowmlp {name} dx{i}", _rel(xs[i].grad, xr[i].grad), exact))
+            else:
+                out.append((f"rowmlp {name} dx{i} absent", 0.0 if xs[i].grad is None else 1.0, 0.0))
+    # batch invariance: a row computed alone equals the same row computed inside a batch, bit for bit
+    x = _r(250, 500, scale=0.5, seed=130)
+    heads = [[_r(500, 500, scale=0.05, seed=131), _r(500, seed=132), _r(500, 500, scale=0.05, seed=133), _r(500, seed=134)]]
+    with torch.no_grad():
+        (yb,) = ops.row_mlp([x], heads, (ops.ACT_NONE,))
+        (y1,) = ops.row_mlp([x[77:78].contiguous()], heads, (ops.ACT_NONE,))
+    out.append(("rowmlp batch invariance (row alone == row in batch)", float((yb[77] - y1[0]).abs().max()), 0.0))
+    return out
+
+
 ALL = [("gemm", check_gemm), ("lstm", check_lstm), ("attention", check_attention), ("small_ops", check_small_ops),
-       ("loss", check_loss), ("optim", check_optim)]
+       ("loss", check_loss), ("optim", check_optim), ("rowmlp", check_rowmlp)]

@@ -18,8 +18,8 @@ class _B:
 
 def _translator(name, gemm_mode):
     import variational_mmt_b200 as vm
-    from variational_mmt_b200 import _lib
-    _lib.lib.vmmt_set_gemm_mode(gemm_mode)
+    from variational_mmt_b200 import _lib, ops
+    ops.set_gemm_mode(gemm_mode)
     meta, arr = load_golden(name)
     cfg = synth.ModelConfig(**meta["cfg"])
     params = synth.make_params(cfg, meta["param_seed"], meta["param_scale"])
@@ -46,7 +46,7 @@ def _check(ret, j, arr, i, tol):
 @pytest.mark.parametrize("name", ["tiny_cond_beam5", "tiny_cond_greedy", "tiny_fixed_beam5"])
 def test_sentence_by_sentence_matches_reference(name, mode, cuda_device):
     """batch_size 1, as translate_mm_vi.py runs it."""
-    from variational_mmt_b200 import _lib
+    from variational_mmt_b200 import _lib, ops
     try:
         tr, batch, arr, ex = _translator(name, mode)
         for i in range(ex["n_sent"]):
@@ -57,7 +57,7 @@ def test_sentence_by_sentence_matches_reference(name, mode, cuda_device):
             ret = tr.translate_batch(b, None, i)
             _check(ret, 0, arr, i, 1e-4 if mode == 1 else 2e-3)
     finally:
-        _lib.lib.vmmt_set_gemm_mode(0)
+        ops.set_gemm_mode(0)
 
 
 @pytest.mark.parametrize("mode", [1, 0], ids=["fp32_simt", "tf32_tc"])
@@ -66,7 +66,7 @@ def test_sentence_by_sentence_matches_reference(name, mode, cuda_device):
 def test_batched_decode_equals_sentence_by_sentence(name, graph, mode, cuda_device):
     """All sentences of the (padded, length-sorted) batch advance together: new behaviour whose oracle is
     the reference run one sentence at a time."""
-    from variational_mmt_b200 import _lib
+    from variational_mmt_b200 import _lib, ops
     try:
         tr, batch, arr, ex = _translator(name, mode)       # mode 0: fused top-K generator epilogue + tiled beam attention
         tr.poll_every = 1
@@ -79,15 +79,15 @@ def test_batched_decode_equals_sentence_by_sentence(name, graph, mode, cuda_devi
             for i in range(ex["n_sent"]):
                 _check(ret, i, arr, i, 1e-4 if mode == 1 else 2e-3)
     finally:
-        _lib.lib.vmmt_set_gemm_mode(0)
+        ops.set_gemm_mode(0)
 
 
 def test_in_process_validation_translate_equals_sentence_by_sentence(cuda_device, tmp_path):
     """translate_dataset (batched, in place on the live training model) returns, in corpus order, what
     the per-sentence decode of translate_mm_vi.py returns, and restores train mode."""
     import variational_mmt_b200 as vm
-    from variational_mmt_b200 import _lib, io
-    _lib.lib.vmmt_set_gemm_mode(1)
+    from variational_mmt_b200 import _lib, ops, io
+    ops.set_gemm_mode(1)
     try:
         cfg = synth.TINY
         params = synth.make_params(cfg, 3435, 0.1)
@@ -113,7 +113,7 @@ def test_in_process_validation_translate_equals_sentence_by_sentence(cuda_device
             assert hyps[i] == words, f"sentence {i}"
         assert out.read_text().splitlines() == [" ".join(h) for h in hyps]
     finally:
-        _lib.lib.vmmt_set_gemm_mode(0)
+        ops.set_gemm_mode(0)
 
 
 @pytest.mark.parametrize("step,V", [(0, 1000), (3, 1000), (3, 130), (7, 10000)])
@@ -121,7 +121,7 @@ def test_fused_topk_generator_equals_materialised_logprobs(step, V, cuda_device)
     """vmmt_generator_topk + vmmt_beam_advance_topk (per-tile {max, sum exp, top-K} kept by the GEMM epilogue) select the
     same hypotheses as vmmt_generator_logprobs + vmmt_beam_advance on the materialised [K*B, V] log-probs -- including
     finished (EOS) beams, the first step (beam row 0 only) and a ragged last tile."""
-    from variational_mmt_b200 import _lib as L
+    from variational_mmt_b200 import _lib as L, ops
     from variational_mmt_b200._lib import fptr, ptr, stream
     dev = cuda_device
     g = torch.Generator(device="cuda").manual_seed(step * 31 + V)
@@ -130,7 +130,7 @@ def test_fused_topk_generator_equals_materialised_logprobs(step, V, cuda_device)
     x = torch.randn(R, H, device=dev, generator=g)
     W = (torch.rand(V, H, device=dev, generator=g) - 0.5) * 0.4
     bias = (torch.rand(V, device=dev, generator=g) - 0.5) * 0.4
-    assert L.lib.vmmt_generator_topk_supported(fptr(x), fptr(W), R, H, V)
+    assert L.lib.vmmt_generator_topk_supported(fptr(x), fptr(W), R, H, V, 0)
 
     def state():
         st = {}
@@ -156,11 +156,11 @@ def test_fused_topk_generator_equals_materialised_logprobs(step, V, cuda_device)
                 ptr(st["done"]), ptr(st["n_active"]), stream())
     a, f = state(), state()
     logp, lse = torch.empty(R, V, device=dev), torch.empty(R, device=dev)
-    L.call("vmmt_generator_logprobs", fptr(x), fptr(W), fptr(bias), R, H, V, fptr(logp), fptr(lse), stream())
+    L.call("vmmt_generator_logprobs", fptr(x), fptr(W), fptr(bias), R, H, V, fptr(logp), fptr(lse), 0, stream())
     L.call("vmmt_beam_advance", fptr(logp), B, K, V, *tail(a))
     wsb = int(L.lib.vmmt_generator_topk_workspace_bytes(R, V, K))
     ws = torch.zeros(wsb // 4, device=dev)
-    L.call("vmmt_generator_topk", fptr(x), fptr(W), fptr(bias), R, H, V, K, fptr(ws), wsb, stream())
+    L.call("vmmt_generator_topk", fptr(x), fptr(W), fptr(bias), R, H, V, K, fptr(ws), wsb, 0, stream())
     L.call("vmmt_beam_advance_topk", fptr(ws), B, K, V, *tail(f))
     torch.cuda.synchronize()
     for k in ("next_ys", "prev_ks", "tok_cur", "prev_cur", "fin_t", "fin_k", "n_fin", "done", "n_active"):
@@ -170,3 +170,30 @@ def test_fused_topk_generator_equals_materialised_logprobs(step, V, cuda_device)
     # and the materialised path is what torch computes
     ref = torch.log_softmax(x.double() @ W.double().t() + bias.double(), dim=1)
     assert float((logp.double() - ref).abs().max()) < 5e-3          # TF32 operands
+
+
+def test_encoder_and_prior_are_batch_invariant_bitwise(cuda_device):
+    """A sentence alone and the same sentence inside a 250-sentence batch give BITWISE identical encoder context, final
+    state and prior mean (ops.batch_invariant: no split-K; the recurrence pins its rounding order so that the one- and
+    two-row-group instantiations agree; the row-MLP kernel's arithmetic per row does not depend on the row count).
+    The reference decodes one sentence at a time (translate_mm_vi.py:80-82): batching must not change its output."""
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import synthetic, ops
+    opt = synthetic.make_opt(conditional=True, dropout=0.5)
+    fields = synthetic.make_fields(10000, 10000)
+    torch.manual_seed(3435)
+    model = vm.make_vi_model_mmt(opt, fields, gpu=True)
+    model.eval()
+    src, sl, _t, _tl, _img = synthetic.random_batch(10000, 10000, 250, 8, seed=77)
+    src, sl = src.cuda(), sl.cuda()
+    with torch.no_grad(), ops.batch_invariant():
+        (hb, cb), ctx_b = model.encoder(src.unsqueeze(2), sl)
+        zb = model.gen_net_global(ctx_b, sl)[0].mean()
+        for i in [0, 1, 57, 123, 249]:
+            n = int(sl[i])
+            s1 = src[:n, i:i + 1].contiguous()
+            (h1, c1), ctx_1 = model.encoder(s1.unsqueeze(2), sl[i:i + 1].contiguous())
+            z1 = model.gen_net_global(ctx_1, sl[i:i + 1].contiguous())[0].mean()
+            assert torch.equal(ctx_b[:n, i], ctx_1[:, 0]), f"context of sentence {i}"
+            assert torch.equal(hb[:, i], h1[:, 0]) and torch.equal(cb[:, i], c1[:, 0]), f"final state of sentence {i}"
+            assert torch.equal(zb[i], z1[0]), f"prior mean of sentence {i}"

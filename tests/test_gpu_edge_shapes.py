@@ -44,9 +44,9 @@ CASES = {
 @pytest.mark.parametrize("case", list(CASES))
 def test_edge_shape_train_step_matches_oracle(case, conditional, mode, cuda_device):
     import variational_mmt_b200 as vm
-    from variational_mmt_b200 import _lib
+    from variational_mmt_b200 import _lib, ops
     ltol, gtol = (2e-5, 2e-4) if mode == 1 else (1e-3, 3e-2)
-    _lib.lib.vmmt_set_gemm_mode(mode)
+    ops.set_gemm_mode(mode)
     try:
         cfg = synth.ModelConfig(**{**synth.TINY.to_dict(), "conditional": conditional})
         params = synth.make_params(cfg, 3435, 0.1)
@@ -79,4 +79,4 @@ def test_edge_shape_train_step_matches_oracle(case, conditional, mode, cuda_devi
             err = np.linalg.norm(grads[k].astype(np.float64) - og.numpy()) / max(np.linalg.norm(og.numpy()), floor)
             assert err <= gtol, f"grad {k}: rel err {err:.3e}"
     finally:
-        _lib.lib.vmmt_set_gemm_mode(0)
+        ops.set_gemm_mode(0)

@@ -31,11 +31,11 @@ def test_generator_nll_cfg5_shape_matches_torch(cuda_device):
     wsb = int(L.lib.vmmt_generator_workspace_bytes(M, V))
     ws = torch.empty(wsb // 4, device=dev)
     L.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), pad, M, H, V, fptr(lse), fptr(stats), fptr(ws),
-           wsb, stream())
+           wsb, 0, stream())
     dx = torch.empty(M, H, device=dev)
     gs = torch.ones(1, device=dev)
     L.call("vmmt_generator_nll_bwd", fptr(x), fptr(W), fptr(b), ptr(tgt), pad, fptr(lse), fptr(gs), 1.0, M, H, V,
-           fptr(dx), None, None, fptr(ws), wsb, stream())
+           fptr(dx), None, None, fptr(ws), wsb, 0, stream())
     torch.cuda.synchronize()
     # reference in chunks of rows (the [M,V] fp32 log-prob matrix is 5.2 GB; keep the test's footprint small)
     nll, correct, words = 0.0, 0, 0

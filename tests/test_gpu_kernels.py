@@ -8,10 +8,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=["fp32_simt", "tf32_tc"])
 def gemm_mode(request, cuda_device):
-    from variational_mmt_b200 import _lib
-    _lib.lib.vmmt_set_gemm_mode(1 if request.param == "fp32_simt" else 0)
+    from variational_mmt_b200 import _lib, ops
+    ops.set_gemm_mode(1 if request.param == "fp32_simt" else 0)
     yield 1.0 if request.param == "fp32_simt" else 100.0     # TF32 operands: ~1e-3 relative
-    _lib.lib.vmmt_set_gemm_mode(0)
+    ops.set_gemm_mode(0)
 
 
 @pytest.mark.parametrize("group", [n for n, _ in kc.ALL])

@@ -23,11 +23,11 @@ MODES = {"fp32_simt": (1, 2e-5, 2e-5, 2e-4), "tf32_tc": (0, 1e-3, 1e-3, 3e-2)}
 
 @pytest.fixture(params=list(MODES))
 def mode(request, cuda_device):
-    from variational_mmt_b200 import _lib
+    from variational_mmt_b200 import _lib, ops
     gm, *tols = MODES[request.param]
-    _lib.lib.vmmt_set_gemm_mode(gm)
+    ops.set_gemm_mode(gm)
     yield tols
-    _lib.lib.vmmt_set_gemm_mode(0)
+    ops.set_gemm_mode(0)
 
 
 def _setup(name):

@@ -17,6 +17,6 @@ wsb = _lib.lib.vmmt_generator_workspace_bytes(M, V)
 ws = torch.empty(wsb // 4, device=dev)
 for _ in range(3):
     _lib.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), 1, M, H, V, fptr(lse), fptr(stats),
-              fptr(ws), wsb, stream())
+              fptr(ws), wsb, 0, stream())
 torch.cuda.synchronize()
 print("ok", stats.tolist())

@@ -10,11 +10,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import kernel_checks as kc  # noqa: E402
-from variational_mmt_b200 import _lib  # noqa: E402
+from variational_mmt_b200 import _lib, ops  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "simt"
 groups = set(sys.argv[2:])
-_lib.lib.vmmt_set_gemm_mode(1 if mode == "simt" else 0)
+ops.set_gemm_mode(1 if mode == "simt" else 0)
 scale = 1.0 if mode == "simt" else 100.0
 bad = 0
 for name, fn in kc.ALL:

@@ -19,18 +19,21 @@ from oracle import vi_model1_ref as R
 
 def probe(name, gemm_mode, dtype_mode="f32"):
     import variational_mmt_b200 as vm
-    from variational_mmt_b200 import _lib
+    from variational_mmt_b200 import _lib, ops
     meta, arr = load_golden(name)
     cfg = synth.ModelConfig(**meta["cfg"])
     params = synth.make_params(cfg, meta["param_seed"], meta["param_scale"])
     batch = synth.make_batch(cfg, **meta["batch"])
     train = name.endswith("train")
-    _lib.lib.vmmt_set_gemm_mode(gemm_mode)
+    ops.set_gemm_mode(gemm_mode)
     if hasattr(vm, "set_compute_dtype"):
         vm.set_compute_dtype(dtype_mode)
     try:
         model, fields = build_cuda_model(cfg, params)
         model.train(train)
+        cap = {}
+        model.encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("context", o[1].detach()))
+        model.decoder.rnn.register_forward_hook(lambda m, i, o: cap.__setitem__("rnn_out", o[0].detach()))
         b = to_device(batch)
         loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
         if train:
@@ -45,7 +48,7 @@ def probe(name, gemm_mode, dtype_mode="f32"):
                 st = loss.monolithic_compute_loss(b, out, attns)
             ofwd, ostats, _ = R.eval_step(params, cfg, batch)
     finally:
-        _lib.lib.vmmt_set_gemm_mode(0)
+        ops.set_gemm_mode(0)
         if hasattr(vm, "set_compute_dtype"):
             vm.set_compute_dtype("f32")
     a = attns["std"].detach().cpu().numpy().astype(np.float64)
@@ -62,6 +65,14 @@ def probe(name, gemm_mode, dtype_mode="f32"):
                nll_rel=abs(st.nmt_loss - ostats["nmt"]) / abs(ostats["nmt"]),
                kl_rel=abs(st.td_kl_before - ostats["td_kl_before"]) / abs(ostats["td_kl_before"]),
                img_rel=abs(st.image_feats_loss - ostats["img_feats_loss"]) / abs(ostats["img_feats_loss"]))
+    for k in ("context", "rnn_out"):
+        res[k + "_max_abs"] = float(np.abs(cap[k].cpu().numpy() - ofwd[k].detach().numpy()).max())
+    if "--per-step" in sys.argv:
+        for k in ("context", "rnn_out"):
+            e = np.abs(cap[k].cpu().numpy() - ofwd[k].detach().numpy()).max(axis=(1, 2))
+            res[k + "_err_by_t"] = [float("%.2e" % v) for v in e]
+            res[k + "_absmax_by_t"] = [float("%.2e" % v) for v in np.abs(ofwd[k].detach().numpy()).max(axis=(1, 2))]
+    res["z_max_abs"] = float(np.abs(attns["z0_sample"][0].detach().cpu().numpy() - ofwd["z"].detach().numpy()).max())
     for k in ("mu_q", "sd_q", "mu_p", "sd_p"):
         src = attns["z_latent"][0] if k.endswith("q") else attns["p_latent"][0]
         v = src.params()[0 if k.startswith("mu") else 1].detach().cpu().numpy()

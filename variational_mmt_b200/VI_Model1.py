@@ -21,7 +21,9 @@ class StdRNNVIModel1Decoder(RNNVIDecoderBase):
         assert kwargs["image_features"] is None, "Model 'vi-model1' does not use image features in the decoder!"
         E = self.embeddings.embedding_size
         w0 = self.rnn.weight_ih_l0
-        zb = ops.linear(z_sample.detach(), w0, cols=(E, E + self.latent_dim))     # [B,4H]
+        # [B,4H]; exact fp32 over the batch rows: z is O(1) (embeddings are O(0.1)) and this term enters EVERY step of the
+        # recurrence, so a TF32 rounding error here accumulates linearly in the cell state (measured, tools/parity_probe.py)
+        zb = ops.linear(z_sample.detach(), w0, cols=(E, E + self.latent_dim), rowwise=True)
         gx0 = kwargs.get("input_projection")
         if gx0 is None:
             emb = self.embeddings(input)                                       # [T,B,E]

@@ -14,7 +14,7 @@ from .Optim import Optim
 from .ModelConstructor import make_vi_model_mmt, Generator
 from .modules import (Embeddings, LSTM, GlobalAttention, Normal, LocationLayer, ScaleLayer,
                       GlobalInferenceNetwork, GlobalFullInferenceNetwork, ImageGlobalInferenceNetwork)
-from .ops import manual_seed
+from .ops import manual_seed, set_gemm_mode, get_gemm_mode
 from .graph import GraphedTrainStep
 from . import translate, distributed, io
 from .translate import TranslatorMultimodalVI, GNMTGlobalScorer

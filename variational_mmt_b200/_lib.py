@@ -35,23 +35,29 @@ class LstmDirBwd(C.Structure):
                 ("reverse", C.c_int32), ("pad_", C.c_int32)]
 
 
+class RowLinSeg(C.Structure):
+    _fields_ = [("p", P), ("ld", L), ("k0", C.c_int32), ("pad_", C.c_int32)]
+
+
+class RowLin(C.Structure):
+    _fields_ = [("seg", RowLinSeg * 3), ("nseg", C.c_int32), ("act", C.c_int32), ("y", P), ("ldy", L),
+                ("yact", C.c_int32), ("pad_", C.c_int32), ("w", P), ("ldw", L), ("bias", P), ("out", P), ("ldo", L),
+                ("xt_out", P), ("ld_xt", L)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/vmmt.h
 SIGNATURES = {
     "vmmt_last_error": (C.c_char_p, []),
     "vmmt_version": (I, []),
     "vmmt_launch_count": (C.c_ulonglong, []),
-    "vmmt_set_gemm_mode": (None, [I]),
-    "vmmt_get_gemm_mode": (I, []),
-    "vmmt_gemm_set_background": (None, [I]),
-    "vmmt_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, P]),
-    "vmmt_gemm_dual": (I, [P, L, P, L, I, P, L, P, L, I, P, L, I, I, P, I, P]),
+    "vmmt_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, I, P]),
+    "vmmt_gemm_dual": (I, [P, L, P, L, I, P, L, P, L, I, P, L, I, I, P, I, I, P]),
     "vmmt_embedding_fwd": (I, [P, L, P, I, P, P]),
     "vmmt_embedding_bwd": (I, [P, L, P, I, L, P, P]),
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_lstm_seq_supported": (I, [I, I, I]),
-    "vmmt_lstm_set_cluster_budget": (None, [I]),
-    "vmmt_lstm_seq_fwd": (I, [C.POINTER(LstmDir), I, P, I, I, I, P, SZ, P]),
-    "vmmt_lstm_seq_bwd": (I, [C.POINTER(LstmDirBwd), I, P, I, I, I, P, SZ, P]),
+    "vmmt_lstm_seq_fwd": (I, [C.POINTER(LstmDir), I, P, I, I, I, I, I, P, SZ, P]),
+    "vmmt_lstm_seq_bwd": (I, [C.POINTER(LstmDirBwd), I, P, I, I, I, I, I, P, SZ, P]),
     "vmmt_lstm_cell_fwd": (I, [P, P, P, P, P, P, P, I, I, P]),
     "vmmt_attention_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "vmmt_attention_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P]),
@@ -66,18 +72,19 @@ SIGNATURES = {
     "vmmt_normal_sample": (I, [P, P, P, P, L, U64, U64, P, P]),
     "vmmt_kl_fwd": (I, [P, P, P, P, P, I, I, P]),
     "vmmt_kl_bwd": (I, [P, P, P, P, P, P, P, P, P, F, I, I, P]),
+    "vmmt_rowlin": (I, [C.POINTER(RowLin), I, I, I, I, I, I, P]),
     "vmmt_gate_fwd": (I, [P, P, P, P, P, I, I, P]),
     "vmmt_gate_bwd": (I, [P, P, P, P, P, P, I, I, P]),
     "vmmt_image_loss_fwd": (I, [P, P, P, P, I, I, P]),
     "vmmt_image_loss_bwd": (I, [P, P, P, P, P, F, I, I, I, P]),
     "vmmt_generator_workspace_bytes": (SZ, [I, I]),
-    "vmmt_generator_nll_fwd": (I, [P, P, P, P, L, I, I, I, P, P, P, SZ, P]),
-    "vmmt_generator_nll_bwd": (I, [P, P, P, P, L, P, P, F, I, I, I, P, P, P, P, SZ, P]),
-    "vmmt_generator_nll_wgrad": (I, [P, P, I, I, I, P, P, P]),
-    "vmmt_generator_logprobs": (I, [P, P, P, I, I, I, P, P, P]),
+    "vmmt_generator_nll_fwd": (I, [P, P, P, P, L, I, I, I, P, P, P, SZ, I, P]),
+    "vmmt_generator_nll_bwd": (I, [P, P, P, P, L, P, P, F, I, I, I, P, P, P, P, SZ, I, P]),
+    "vmmt_generator_nll_wgrad": (I, [P, P, I, I, I, P, P, I, P]),
+    "vmmt_generator_logprobs": (I, [P, P, P, I, I, I, P, P, I, P]),
     "vmmt_generator_topk_workspace_bytes": (SZ, [I, I, I]),
-    "vmmt_generator_topk_supported": (I, [P, P, I, I, I]),
-    "vmmt_generator_topk": (I, [P, P, P, I, I, I, I, P, SZ, P]),
+    "vmmt_generator_topk_supported": (I, [P, P, I, I, I, I]),
+    "vmmt_generator_topk": (I, [P, P, P, I, I, I, I, P, SZ, I, P]),
     "vmmt_fill_zero": (I, [P, L, I, P]),
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),
@@ -106,6 +113,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SOFTPLUS, ACT_SIGMOID = range(5)
+F_EXACT, F_BF16, F_BACKGROUND, F_NO_SPLITK = 1, 2, 4, 8          # include/vmmt.h VMMT_F_*
 
 
 def last_error():

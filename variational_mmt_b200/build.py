@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvmmt.so")
-SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm.cu", "lstm_tc.cu", "lstm_step.cu", "attention.cu", "elementwise.cu",
+SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm.cu", "lstm_tc.cu", "lstm_step.cu", "attention.cu", "elementwise.cu", "rowlin.cu",
            "generator.cu", "optim.cu", "decode.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

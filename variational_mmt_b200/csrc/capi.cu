@@ -12,7 +12,6 @@ thread_local char g_err[512] = "";
 std::mutex g_mu;
 int g_sms[64];
 bool g_sms_init = false;
-int g_gemm_mode = -1;   // -1 unread, 0 = auto (tcgen05 when eligible), 1 = force SIMT fp32
 }
 
 void vmmt_set_error(const char* fmt, ...) {
@@ -51,19 +50,9 @@ int vmmt_num_sms() {
 extern "C" const char* vmmt_last_error(void) { return g_err; }
 extern "C" int vmmt_version(void) { return 100; }
 
-// 0 = auto, 1 = exact-fp32 SIMT everywhere (parity debugging; also env VMMT_GEMM=simt)
-extern "C" void vmmt_set_gemm_mode(int mode) { g_gemm_mode = mode; }
-extern "C" int vmmt_get_gemm_mode(void) {
-  if (g_gemm_mode < 0) {
-    const char* e = getenv("VMMT_GEMM");
-    g_gemm_mode = (e && strcmp(e, "simt") == 0) ? 1 : 0;
-  }
-  return g_gemm_mode;
-}
-
 extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb,
                          int b_kmajor, float* C, int64_t ldc, int M, int N, int K, const float* bias,
-                         int act, int accumulate, void* stream) {
+                         int act, int accumulate, int flags, void* stream) {
   VMMT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dims");
   VMMT_REQUIRE(A && B && C, "gemm: null operand");
   cudaStream_t s = (cudaStream_t)stream;
@@ -72,11 +61,11 @@ extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float*
     fprintf(stderr, "[vmmt_gemm] M=%d N=%d K=%d lda=%lld(%s) ldb=%lld(%s) ldc=%lld bias=%d act=%d acc=%d -> %s\n", M, N, K,
             (long long)lda, a_kmajor ? "k" : "mn", (long long)ldb, b_kmajor ? "k" : "mn", (long long)ldc, bias != nullptr,
             act, accumulate,
-            (vmmt_get_gemm_mode() == 0 && vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K))
+            (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K))
                 ? "tcgen05" : "simt");
-  if (vmmt_get_gemm_mode() == 0 &&
+  if (!(flags & VMMT_F_EXACT) &&
       vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K)) {
-    return vmmt_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);
+    return vmmt_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, flags, s);
   }
   return vmmt_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);
 }
@@ -85,17 +74,17 @@ extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float*
 // epilogue).  Falls back to two vmmt_gemm calls when the tensor-core kernel does not apply.
 extern "C" int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, int64_t ldb1, int K1,
                               const float* A2, int64_t lda2, const float* B2, int64_t ldb2, int K2, float* C,
-                              int64_t ldc, int M, int N, const float* bias, int act, void* stream) {
+                              int64_t ldc, int M, int N, const float* bias, int act, int flags, void* stream) {
   VMMT_REQUIRE(M >= 0 && N >= 0 && K1 >= 1 && K2 >= 1, "gemm_dual: bad dims");
   VMMT_REQUIRE(A1 && B1 && A2 && B2 && C, "gemm_dual: null operand");
   cudaStream_t s = (cudaStream_t)stream;
-  if (vmmt_get_gemm_mode() == 0 && vmmt_gemm_tc_eligible(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1) &&
+  if (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1) &&
       vmmt_gemm_tc_eligible(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2)) {
     // each pair has its own tensor maps, so a ragged K tail of either is zero-filled by the TMA independently
     VmmtGemmSecond second{A2, lda2, B2, ldb2, K2};
-    return vmmt_gemm_tc_dual(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, act, 0, nullptr, &second, s);
+    return vmmt_gemm_tc_dual(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, act, 0, nullptr, &second, flags, s);
   }
-  int rc = vmmt_gemm(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, VMMT_ACT_NONE, 0, stream);
+  int rc = vmmt_gemm(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, VMMT_ACT_NONE, 0, flags, stream);
   if (rc) return rc;
-  return vmmt_gemm(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2, nullptr, act, act == VMMT_ACT_NONE ? 1 : 2, stream);
+  return vmmt_gemm(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2, nullptr, act, act == VMMT_ACT_NONE ? 1 : 2, flags, stream);
 }

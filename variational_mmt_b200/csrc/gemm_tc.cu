@@ -669,9 +669,6 @@ int launch_major(bool a_mn, bool b_mn, const Maps& m, const GemmArgs& g, dim3 gr
 
 }  // namespace
 
-static int g_background = 0;
-extern "C" void vmmt_gemm_set_background(int on) { g_background = on; }
-
 bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
                            const float* C, int64_t ldc, int M, int N, int K) {
   (void)C; (void)ldc; (void)a_kmajor; (void)b_kmajor;
@@ -688,20 +685,21 @@ bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const floa
 }
 
 int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
-                 int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate, cudaStream_t s) {
-  return vmmt_gemm_tc_ex(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, nullptr, s);
+                 int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate, int flags, cudaStream_t s) {
+  return vmmt_gemm_tc_ex(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, nullptr, flags, s);
 }
 
 int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
                     int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
-                    const VmmtGenEpi* epi, cudaStream_t s) {
-  return vmmt_gemm_tc_dual(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, epi, nullptr, s);
+                    const VmmtGenEpi* epi, int flags, cudaStream_t s) {
+  return vmmt_gemm_tc_dual(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, epi, nullptr, flags, s);
 }
 
 int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
                       int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
-                      const VmmtGenEpi* epi, const VmmtGemmSecond* second, cudaStream_t s) {
+                      const VmmtGenEpi* epi, const VmmtGemmSecond* second, int flags, cudaStream_t s) {
   const bool a_mn = !a_kmajor, b_mn = !b_kmajor;
+  const bool background = (flags & VMMT_F_BACKGROUND) != 0;
   const int nsm = vmmt_num_sms();
   const int tiles_m = ceil_div(M, BM);
   const int nkb2 = second ? ceil_div(second->K2, BK) : 0;
@@ -710,7 +708,9 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   // (tile width, split-K) from a small cost model in SM cycles: a CTA costs a fixed prologue + epilogue plus
   // its k-blocks; 128-wide tiles run one CTA per SM (shared-memory-bandwidth bound, ~450 cycles per k-block),
   // 64-wide tiles two per SM; split-K needs a linear epilogue (an activation is applied by a finishing pass)
-  const bool can_split = epi == nullptr && second == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
+  // VMMT_F_NO_SPLITK: one accumulation chain per output element in fixed K order (deterministic; a row's result does not
+  // depend on how many rows the call has: inference compares a sentence decoded alone with the same sentence in a batch)
+  const bool can_split = !(flags & VMMT_F_NO_SPLITK) && epi == nullptr && second == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
   int BN = 128, splits = 1;
   double best = 1e30;
   for (int bn = (epi ? 128 : 64); bn <= 128; bn *= 2) {
@@ -787,7 +787,7 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   // its SM for the whole GEMM, and a recurrence kernel launched meanwhile cannot place its 16-CTA clusters until the GEMM
   // ends (measured: +80..100 us on an encoder layer's backward, at random); short-lived CTAs drain within one tile time
   // and the higher-priority cluster launch gets the SMs.
-  dim3 grid((splits > 1 || no_persist || g_background) ? tiles : min(tiles, slots), 1, splits);
+  dim3 grid((splits > 1 || no_persist || background) ? tiles : min(tiles, slots), 1, splits);
   static long long* trace_buf = nullptr;
   const bool tracing = getenv("VMMT_GEMM_TRACE") != nullptr;
   if (tracing) {

@@ -134,10 +134,10 @@ __global__ void logprob_kernel(float* __restrict__ logits, const float* __restri
 }  // namespace
 
 extern "C" int vmmt_gemm(const float*, int64_t, int, const float*, int64_t, int, float*, int64_t,
-                         int, int, int, const float*, int, int, void*);
+                         int, int, int, const float*, int, int, int, void*);
 
 extern "C" int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW,
-                                        float* db, void* stream);
+                                        float* db, int flags, void* stream);
 
 extern "C" size_t vmmt_generator_workspace_bytes(int M, int V) {
   return ((size_t)M * V + (size_t)M * 4) * sizeof(float);
@@ -146,7 +146,7 @@ extern "C" size_t vmmt_generator_workspace_bytes(int M, int V) {
 extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b,
                                       const int64_t* target, int64_t pad_idx, int M, int H, int V,
                                       float* lse, float* stats3, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      size_t workspace_bytes, int flags, void* stream) {
   if (workspace_bytes < vmmt_generator_workspace_bytes(M, V)) {
     vmmt_set_error("generator_nll_fwd: workspace too small");
     return VMMT_EWORKSPACE;
@@ -156,13 +156,13 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
   int rc;
   // tensor-core mode: log-sum-exp / target logit / argmax are folded into the GEMM epilogue; the logits of a tile
   // live in tensor memory and registers only.  Partials: [ceil(V/128)][M] float4 at the head of the workspace.
-  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_GEN_UNFUSED") &&
+  if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_GEN_UNFUSED") &&
       vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) {
     const int ntile = ceil_div(V, 128);
     float* part = logits;                                  // ntile * M * 4 floats  <<  M * V
     float* tgt_logit = part + (size_t)ntile * M * 4;
     VmmtGenEpi epi{1, part, tgt_logit, target, nullptr, nullptr, 1.0f, (long long)pad_idx};
-    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, (cudaStream_t)stream);
+    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, (cudaStream_t)stream);
     if (rc) return rc;
     lse_combine_kernel<<<ceil_div(M, 4), 128, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(part), tgt_logit, target, pad_idx, M, ntile, lse, rowstat);
@@ -171,7 +171,7 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
     reduce_rowstat_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowstat, M, stats3);
     return vmmt_check_launch("reduce_rowstat");
   }
-  rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+  rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, flags, stream);
   if (rc) return rc;
   row_lse_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, target, pad_idx, lse, rowstat, V);
   rc = vmmt_check_launch("row_lse");
@@ -183,7 +183,7 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
 extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const float* b,
                                       const int64_t* target, int64_t pad_idx, const float* lse,
                                       const float* gscale, float scale, int M, int H, int V, float* dx, float* dW,
-                                      float* db, void* workspace, size_t workspace_bytes,
+                                      float* db, void* workspace, size_t workspace_bytes, int flags,
                                       void* stream) {
   if (workspace_bytes < vmmt_generator_workspace_bytes(M, V)) {
     vmmt_set_error("generator_nll_bwd: workspace too small");
@@ -193,33 +193,33 @@ extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const floa
   cudaStream_t s = (cudaStream_t)stream;
   int rc = VMMT_EINVAL;
   // tensor-core mode: the recomputed logits are turned into dlogits in the GEMM epilogue (one pass over M x V)
-  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_GEN_UNFUSED") && (V & 3) == 0 &&
+  if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_GEN_UNFUSED") && (V & 3) == 0 &&
       vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, dl, V, M, V, H)) {
     VmmtGenEpi epi{2, nullptr, nullptr, target, lse, gscale, scale, (long long)pad_idx};
-    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, s);
+    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, s);
   }
   if (rc != VMMT_OK) {
-    rc = vmmt_gemm(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+    rc = vmmt_gemm(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, flags, stream);
     if (rc) return rc;
     dlogits_kernel<<<dim3(ceil_div(V, 256), M), 256, 0, s>>>(dl, lse, target, pad_idx, gscale, scale, V);
     rc = vmmt_check_launch("dlogits");
     if (rc) return rc;
   }
   if (dx) {   // dX[M,H] = dl[M,V] W[V,H]
-    rc = vmmt_gemm(dl, V, 1, W, H, 0, dx, H, M, H, V, nullptr, VMMT_ACT_NONE, 0, stream);
+    rc = vmmt_gemm(dl, V, 1, W, H, 0, dx, H, M, H, V, nullptr, VMMT_ACT_NONE, 0, flags, stream);
     if (rc) return rc;
   }
   if (dW == nullptr && db == nullptr) return VMMT_OK;      // weight gradients taken later by vmmt_generator_nll_wgrad
-  return vmmt_generator_nll_wgrad(x, workspace, M, H, V, dW, db, stream);
+  return vmmt_generator_nll_wgrad(x, workspace, M, H, V, dW, db, flags, stream);
 }
 
 // dW[V,H] += dl^T[V,M] x[M,H];  db += colsum(dl), with dl = the dlogits vmmt_generator_nll_bwd left in `workspace`
 // (lets the caller put the weight gradient on another stream, off the critical path of the backward pass)
 extern "C" int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW,
-                                        float* db, void* stream) {
+                                        float* db, int flags, void* stream) {
   const float* dl = (const float*)workspace;
   if (dW) {
-    int rc = vmmt_gemm(dl, V, 0, x, H, 0, dW, H, V, H, M, nullptr, VMMT_ACT_NONE, 1, stream);
+    int rc = vmmt_gemm(dl, V, 0, x, H, 0, dW, H, V, H, M, nullptr, VMMT_ACT_NONE, 1, flags, stream);
     if (rc) return rc;
   }
   if (db) return vmmt_colsum_acc(dl, V, M, V, db, nullptr, stream);
@@ -227,8 +227,8 @@ extern "C" int vmmt_generator_nll_wgrad(const float* x, const void* workspace, i
 }
 
 extern "C" int vmmt_generator_logprobs(const float* x, const float* W, const float* b, int M, int H,
-                                       int V, float* out, float* lse_ws, void* stream) {
-  int rc = vmmt_gemm(x, H, 1, W, H, 1, out, V, M, V, H, b, VMMT_ACT_NONE, 0, stream);
+                                       int V, float* out, float* lse_ws, int flags, void* stream) {
+  int rc = vmmt_gemm(x, H, 1, W, H, 1, out, V, M, V, H, b, VMMT_ACT_NONE, 0, flags, stream);
   if (rc) return rc;
   row_lse_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(out, nullptr, 0, lse_ws, nullptr, V);
   rc = vmmt_check_launch("row_lse");
@@ -244,19 +244,19 @@ extern "C" size_t vmmt_generator_topk_workspace_bytes(int M, int V, int K) {
   return ntile * (size_t)M * (size_t)(1 + K) * sizeof(float2);
 }
 
-extern "C" int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V) {
-  return (vmmt_get_gemm_mode() == 0 && vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) ? 1 : 0;
+extern "C" int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V, int flags) {
+  return (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) ? 1 : 0;
 }
 
 extern "C" int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, int H, int V, int K,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   void* workspace, size_t workspace_bytes, int flags, void* stream) {
   VMMT_REQUIRE(K >= 1 && K <= VMMT_TOPK_MAX, "generator_topk: K = %d outside [1,%d]", K, VMMT_TOPK_MAX);
   if (workspace_bytes < vmmt_generator_topk_workspace_bytes(M, V, K)) {
     vmmt_set_error("generator_topk: workspace too small");
     return VMMT_EWORKSPACE;
   }
-  VMMT_REQUIRE(vmmt_generator_topk_supported(x, W, M, H, V),
-               "generator_topk: needs the tensor-core GEMM (gemm mode 0, 16-byte aligned operands, H %% 4 == 0, V,H >= 64)");
+  VMMT_REQUIRE(vmmt_generator_topk_supported(x, W, M, H, V, flags),
+               "generator_topk: needs the tensor-core GEMM (no VMMT_F_EXACT, 16-byte aligned operands, H %% 4 == 0, V,H >= 64)");
   const size_t ntile = (size_t)ceil_div(V, 128);
   float* tile_lse = (float*)workspace;
   float* tile_cand = tile_lse + ntile * (size_t)M * 2;
@@ -264,5 +264,5 @@ extern "C" int vmmt_generator_topk(const float* x, const float* W, const float* 
   epi.topk = K;
   epi.tile_lse = tile_lse;
   epi.tile_cand = tile_cand;
-  return vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, (cudaStream_t)stream);
+  return vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, (cudaStream_t)stream);
 }

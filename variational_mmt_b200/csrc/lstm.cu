@@ -414,14 +414,14 @@ extern "C" int vmmt_lstm_seq_supported(int ndir, int N, int H) {
 }
 
 extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T,
-                                 int N, int H, void* workspace, size_t workspace_bytes,
+                                 int N, int H, int flags, int cluster_budget, void* workspace, size_t workspace_bytes,
                                  void* stream) {
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_fwd: ndir must be 1 or 2 (got %d)", ndir);
   VMMT_REQUIRE(T > 0 && N > 0 && H > 0, "lstm_seq_fwd: bad dims T=%d N=%d H=%d", T, N, H);
-  // tensor-core cluster path (default); VMMT_GEMM=simt / vmmt_set_gemm_mode(1) selects the exact-fp32 SIMT kernels
-  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_STEPWISE") &&
+  // tensor-core cluster path (default); VMMT_F_EXACT selects the exact-fp32 SIMT kernels
+  if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_STEPWISE") &&
       vmmt_lstm_tc_supported(ndir, N, H))
-    return vmmt_lstm_tc_fwd(dirs, ndir, lengths, T, N, H, (cudaStream_t)stream);
+    return vmmt_lstm_tc_fwd(dirs, ndir, lengths, T, N, H, cluster_budget, (cudaStream_t)stream);
   if (workspace_bytes < vmmt_lstm_workspace_bytes(ndir, N, H)) {
     vmmt_set_error("lstm_seq_fwd: workspace too small");
     return VMMT_EWORKSPACE;
@@ -429,7 +429,7 @@ extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_
   Plan p;
   // large batch / hidden size: one GEMM + one cell kernel per step (lstm_step.cu)
   if (getenv("VMMT_LSTM_STEPWISE") || make_plan(false, ndir, N, H, &p) != VMMT_OK)
-    return vmmt_lstm_step_fwd(dirs, ndir, lengths, T, N, H,
+    return vmmt_lstm_step_fwd(dirs, ndir, lengths, T, N, H, flags,
                               reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + CTR_BYTES), (cudaStream_t)stream);
   cudaStream_t s = (cudaStream_t)stream;
   VMMT_CUDA(cudaMemsetAsync(workspace, 0, CTR_BYTES, s));
@@ -448,18 +448,19 @@ extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_
 }
 
 extern "C" int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths,
-                                 int T, int N, int H, void* workspace, size_t workspace_bytes, void* stream) {
+                                 int T, int N, int H, int flags, int cluster_budget, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_bwd: ndir must be 1 or 2 (got %d)", ndir);
-  if (vmmt_get_gemm_mode() == 0 && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_SIMT_BWD") &&
+  if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_SIMT_BWD") &&
       !getenv("VMMT_LSTM_STEPWISE") && vmmt_lstm_tc_supported(ndir, N, H))
-    return vmmt_lstm_tc_bwd(dirs, ndir, lengths, T, N, H, (cudaStream_t)stream);
+    return vmmt_lstm_tc_bwd(dirs, ndir, lengths, T, N, H, cluster_budget, (cudaStream_t)stream);
   if (workspace_bytes < vmmt_lstm_workspace_bytes(ndir, N, H)) {
     vmmt_set_error("lstm_seq_bwd: workspace too small");
     return VMMT_EWORKSPACE;
   }
   Plan p;
   if (getenv("VMMT_LSTM_STEPWISE") || make_plan(true, ndir, N, H, &p) != VMMT_OK)
-    return vmmt_lstm_step_bwd(dirs, ndir, lengths, T, N, H,
+    return vmmt_lstm_step_bwd(dirs, ndir, lengths, T, N, H, flags,
                               reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + CTR_BYTES), (cudaStream_t)stream);
   cudaStream_t s = (cudaStream_t)stream;
   VMMT_CUDA(cudaMemsetAsync(workspace, 0, CTR_BYTES, s));

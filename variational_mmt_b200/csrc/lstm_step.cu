@@ -10,7 +10,7 @@
 #include "lstm_tc.h"
 
 extern "C" int vmmt_gemm(const float*, int64_t, int, const float*, int64_t, int, float*, int64_t, int, int, int,
-                         const float*, int, int, void*);
+                         const float*, int, int, int, void*);
 
 namespace {
 
@@ -89,8 +89,8 @@ int copy_or_zero(float* dst, const float* src, int64_t n, cudaStream_t s) {
 
 size_t vmmt_lstm_step_workspace_floats(int ndir, int N, int H) { return (size_t)ndir * 6 * N * H; }
 
-int vmmt_lstm_step_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, float* ws,
-                       cudaStream_t s) {
+int vmmt_lstm_step_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int flags,
+                       float* ws, cudaStream_t s) {
   const int64_t NH = (int64_t)N * H;
   for (int d = 0; d < ndir; ++d) {
     const VmmtLstmDir& D = dirs[d];
@@ -105,7 +105,7 @@ int vmmt_lstm_step_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths
       const int t = D.reverse ? T - 1 - st : st;
       const bool have_h = st > 0 || D.h0 != nullptr;
       if (have_h) {
-        rc = vmmt_gemm(hst, H, 1, D.w_hh, H, 1, gpre, 4 * H, N, 4 * H, H, nullptr, VMMT_ACT_NONE, 0, (void*)s);
+        rc = vmmt_gemm(hst, H, 1, D.w_hh, H, 1, gpre, 4 * H, N, 4 * H, H, nullptr, VMMT_ACT_NONE, 0, flags, (void*)s);
         if (rc) return rc;
       }
       lstm_step_fwd_kernel<<<ceil_div(NH, 256), 256, 0, s>>>(
@@ -121,8 +121,8 @@ int vmmt_lstm_step_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths
   return VMMT_OK;
 }
 
-int vmmt_lstm_step_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, float* ws,
-                       cudaStream_t s) {
+int vmmt_lstm_step_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int flags,
+                       float* ws, cudaStream_t s) {
   const int64_t NH = (int64_t)N * H;
   for (int d = 0; d < ndir; ++d) {
     const VmmtLstmDirBwd& D = dirs[d];
@@ -143,7 +143,7 @@ int vmmt_lstm_step_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* leng
       rc = vmmt_check_launch("lstm_step_bwd");
       if (rc) return rc;
       if (st + 1 < T || D.dh0) {                        // dh_{t-1} += dG_t W_hh   ([N,4H] x [4H,H])
-        rc = vmmt_gemm(dg_t, 4 * H, 1, D.w_hh, H, 0, dh, H, N, H, 4 * H, nullptr, VMMT_ACT_NONE, 1, (void*)s);
+        rc = vmmt_gemm(dg_t, 4 * H, 1, D.w_hh, H, 0, dh, H, N, H, 4 * H, nullptr, VMMT_ACT_NONE, 1, flags, (void*)s);
         if (rc) return rc;
       }
     }

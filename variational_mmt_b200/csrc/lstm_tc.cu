@@ -177,8 +177,13 @@ __device__ __forceinline__ long long clock_after(float dep) {
 }
 __device__ __forceinline__ float fex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float frcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fsigmoid(float x) { return frcp(1.0f + fex2(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float ftanh(float x) { return 1.0f - 2.0f * frcp(fex2(2.8853900817779268f * x) + 1.0f); }
+// every operation is pinned (__f*_rn is never contracted or re-associated): the NRG = 1 and NRG = 2 instantiations must
+// round identically, or a row's result would depend on how many rows share its cluster (fp32 differences of one ulp are
+// amplified to 2^-11 by the fp16 rounding of h)
+__device__ __forceinline__ float fsigmoid(float x) { return frcp(__fadd_rn(1.0f, fex2(__fmul_rn(-1.4426950408889634f, x)))); }
+__device__ __forceinline__ float ftanh(float x) {
+  return __fmaf_rn(-2.0f, frcp(__fadd_rn(fex2(__fmul_rn(2.8853900817779268f, x)), 1.0f)), 1.0f);
+}
 
 // shared-memory matrix descriptors (sm_100 version bits).
 //   swizzled  : K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO); LBO unused
@@ -399,8 +404,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const size_t j = (size_t)g * H + unit;
-        bias[r][g] = (D.b_ih ? D.b_ih[j] : 0.f) + (D.b_hh ? D.b_hh[j] : 0.f) +
-                     (D.rowbias ? D.rowbias[(size_t)gn * 4 * H + j] : 0.f);
+        bias[r][g] = __fadd_rn(__fadd_rn(D.b_ih ? D.b_ih[j] : 0.f, D.b_hh ? D.b_hh[j] : 0.f),
+                               D.rowbias ? D.rowbias[(size_t)gn * 4 * H + j] : 0.f);
       }
       if (P.lengths) len[r] = (int)P.lengths[gn];
     }
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
 #pragma unroll
       for (int r = 0; r < RM; ++r)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) gx[r][g] = gxn[r][g] + bias[r][g];
+        for (int g = 0; g < 4; ++g) gx[r][g] = __fadd_rn(gxn[r][g], bias[r][g]);
       if (s + 1 < T) load_gx(D.reverse ? T - 2 - s : s + 1);
       if (tr && tid == 0) P.trace[2] = clock64();
       mbar_wait(bar_mma, (uint32_t)(s & 1));
@@ -494,7 +499,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
 #pragma unroll
         for (int n = 0; n < HN; ++n)
           gsm[(q * NPc + hf * HN + n) * 32 + lane] =
-              (__uint_as_float(v[0][n]) + __uint_as_float(v[1][n])) + (__uint_as_float(v[2][n]) + __uint_as_float(v[3][n]));
+              __fadd_rn(__fadd_rn(__uint_as_float(v[0][n]), __uint_as_float(v[1][n])),
+                        __fadd_rn(__uint_as_float(v[2][n]), __uint_as_float(v[3][n])));
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tr && tid == 0) P.trace[4] = clock64();
@@ -503,10 +509,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {                                        // warp-uniform
           const int n = warp + 8 * r;
-          const float Gi = gsm[(0 * NPc + n) * 32 + lane] + gx[r][0];
-          const float Gf = gsm[(1 * NPc + n) * 32 + lane] + gx[r][1];
-          const float Gg = gsm[(2 * NPc + n) * 32 + lane] + gx[r][2];
-          const float Go = gsm[(3 * NPc + n) * 32 + lane] + gx[r][3];
+          const float Gi = __fadd_rn(gsm[(0 * NPc + n) * 32 + lane], gx[r][0]);
+          const float Gf = __fadd_rn(gsm[(1 * NPc + n) * 32 + lane], gx[r][1]);
+          const float Gg = __fadd_rn(gsm[(2 * NPc + n) * 32 + lane], gx[r][2]);
+          const float Go = __fadd_rn(gsm[(3 * NPc + n) * 32 + lane], gx[r][3]);
           if (tr && tid == 0 && r == 0) P.trace[16] = clock_after(Gi + Gf + Gg + Go);
           av[r][0] = fsigmoid(Gi); av[r][1] = fsigmoid(Gf); av[r][2] = ftanh(Gg); av[r][3] = fsigmoid(Go);
         }
@@ -515,8 +521,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {
           const int n = warp + 8 * r;
-          const float cn = av[r][1] * c[r] + av[r][0] * av[r][2];
-          const float hn = av[r][3] * ftanh(cn);
+          const float cn = __fmaf_rn(av[r][1], c[r], __fmul_rn(av[r][0], av[r][2]));
+          const float hn = __fmul_rn(av[r][3], ftanh(cn));
           const bool m = t < len[r];
           c[r] = m ? cn : c[r];
           h[r] = m ? hn : h[r];
@@ -846,7 +852,6 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
 }
 
 struct TcPlan { int C, G, Ng, Kp, nrg; };
-int g_cluster_budget = 0;     // 0 = all co-resident clusters; > 0: cap (two recurrences sharing the GPU on two streams)
 
 size_t fwd_smem(int Kp, int nrg) {
   return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64 +
@@ -901,11 +906,11 @@ bool tc_shape_ok(int ndir, int N, int H) {
 
 // batch groups: as many clusters as can be co-resident (one wave; a cluster of 16 needs a whole GPC), at most 16
 // rows per group; groups of <= 8 rows run the N = 8 variant (half the hand-off bytes)
-void tc_plan(int ndir, int N, int H, int max_clusters, TcPlan* p) {
+void tc_plan(int ndir, int N, int H, int max_clusters, int cluster_budget, TcPlan* p) {
   p->C = ceil_div(H, UC);
   p->Kp = ceil_div(H, 64) * 64;
   const char* e = getenv("VMMT_LSTM_GROUPS");
-  if (g_cluster_budget > 0) max_clusters = min(max_clusters, g_cluster_budget);
+  if (cluster_budget > 0) max_clusters = min(max_clusters, cluster_budget);
   int gmax = e ? atoi(e) : max(1, max_clusters / ndir);
   int G = max(1, min(gmax, N));
   int Ng = ceil_div(N, G);
@@ -981,16 +986,15 @@ int launch_bwd(TcBwdParams& P, const TcPlan& p, int ndir, int maxc, cudaStream_t
 
 bool vmmt_lstm_tc_supported(int ndir, int N, int H) { return tc_shape_ok(ndir, N, H); }
 
-extern "C" void vmmt_lstm_set_cluster_budget(int max_clusters) { g_cluster_budget = max_clusters > 0 ? max_clusters : 0; }
-
-int vmmt_lstm_tc_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, cudaStream_t s) {
+int vmmt_lstm_tc_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int cluster_budget,
+                     cudaStream_t s) {
   if (!tc_shape_ok(ndir, N, H)) return VMMT_EINVAL;
   TcPlan p;
   const int Kp = ceil_div(H, 64) * 64;
   int maxc = 1;
   int rc = prepare_kernel(lstm_tc_fwd_kernel<2>, ceil_div(H, UC), fwd_smem(Kp, 2), &maxc);
   if (rc) return rc;
-  tc_plan(ndir, N, H, maxc, &p);
+  tc_plan(ndir, N, H, maxc, cluster_budget, &p);
   TcFwdParams P;
   for (int d = 0; d < ndir; ++d) P.d[d] = dirs[d];
   if (ndir == 1) P.d[1] = dirs[0];
@@ -1000,13 +1004,14 @@ int vmmt_lstm_tc_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, 
   return p.nrg == 1 ? launch_fwd<1>(P, p, ndir, maxc, s) : launch_fwd<2>(P, p, ndir, maxc, s);
 }
 
-int vmmt_lstm_tc_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, cudaStream_t s) {
+int vmmt_lstm_tc_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int cluster_budget,
+                     cudaStream_t s) {
   if (!tc_shape_ok(ndir, N, H)) return VMMT_EINVAL;
   TcPlan p;
   int maxc = 1;
   int rc = prepare_kernel(lstm_tc_bwd_kernel<2>, ceil_div(H, UC), bwd_smem(2), &maxc);
   if (rc) return rc;
-  tc_plan(ndir, N, H, maxc, &p);
+  tc_plan(ndir, N, H, maxc, cluster_budget, &p);
   TcBwdParams P;
   for (int d = 0; d < ndir; ++d) P.d[d] = dirs[d];
   if (ndir == 1) P.d[1] = dirs[0];

@@ -12,7 +12,7 @@ int vmmt_gemm_simt(const float* A, int64_t lda, int a_kmajor, const float* B, in
 // alignment / size constraints, in which case vmmt_gemm() uses the SIMT kernel.
 int vmmt_gemm_tc(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb,
                  int b_kmajor, float* C, int64_t ldc, int M, int N, int K, const float* bias,
-                 int act, int accumulate, cudaStream_t s);
+                 int act, int accumulate, int flags, cudaStream_t s);
 // fused generator epilogues of the tensor-core GEMM (gemm_tc.cu): mode 1 = per-row log-sum-exp partials per 128-column
 // tile instead of C (C may be null), mode 2 = C receives the softmax-NLL gradient of the logits, mode 3 = per-row, per-tile
 // {max, sum exp} + the tile's top-`topk` logits with their columns (beam search: no [M,V] log-prob matrix at all)
@@ -32,7 +32,7 @@ struct VmmtGenEpi {
 };
 int vmmt_gemm_tc_ex(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
                     int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
-                    const VmmtGenEpi* epi, cudaStream_t s);
+                    const VmmtGenEpi* epi, int flags, cudaStream_t s);
 // optional second operand pair of the tensor-core GEMM: C = act(A B^T + A2 B2^T + bias), all four operands K-major
 // ([rows, K] row-major, the nn.Linear layout); the k-blocks of the second pair extend the same TMEM accumulation.
 struct VmmtGemmSecond {
@@ -42,6 +42,6 @@ struct VmmtGemmSecond {
 };
 int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor, float* C,
                       int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
-                      const VmmtGenEpi* epi, const VmmtGemmSecond* second, cudaStream_t s);
+                      const VmmtGenEpi* epi, const VmmtGemmSecond* second, int flags, cudaStream_t s);
 bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb,
                            int b_kmajor, const float* C, int64_t ldc, int M, int N, int K);

@@ -44,6 +44,24 @@ class ScaleLayer(nn.Module):
         return ops.linear(h, self.fc2.weight, self.fc2.bias, ops.ACT_SOFTPLUS)
 
 
+def _mlp_heads(location, scale=None):
+    h = [(location.fc1.weight, location.fc1.bias, location.fc2.weight, location.fc2.bias)]
+    if scale is not None:
+        h.append((scale.fc1.weight, scale.fc1.bias, scale.fc2.weight, scale.fc2.bias))
+    return h
+
+
+class _LazyCat(object):
+    """The concatenated network input ``h`` the reference returns beside the distribution (never read by its callers,
+    onmt/Models.py:889-930): the row-MLP kernel consumes the parts in place, ``h()`` materialises the concatenation."""
+
+    def __init__(self, parts):
+        self.parts = parts
+
+    def __call__(self):
+        return torch.cat(list(self.parts), -1)
+
+
 class GlobalInferenceNetwork(nn.Module):
     """Z | x ~ N(loc(h), scale(h)), h = masked mean of the source encodings."""
 
@@ -59,7 +77,9 @@ class GlobalInferenceNetwork(nn.Module):
 
     def forward(self, x, x_lengths):
         h = self.encode_seq(x, x_lengths)
-        return Normal(self.location(h), self.scale(h)), h
+        # both MLPs in exact fp32 over the batch rows: two launches (csrc/rowlin.cu)
+        loc, scale = ops.row_mlp([h], _mlp_heads(self.location, self.scale), (ops.ACT_NONE, ops.ACT_SOFTPLUS))
+        return Normal(loc, scale), h
 
 
 class GlobalFullInferenceNetwork(GlobalInferenceNetwork):
@@ -74,14 +94,10 @@ class GlobalFullInferenceNetwork(GlobalInferenceNetwork):
     def forward(self, x, x_lengths, y, y_lengths, v):
         hx = self.encode_seq(x, x_lengths)
         hy = self.encode_seq(y, y_lengths)
-        h = torch.cat([hx, hy, v], -1)
-        # q(z|x,y,v) sits on the step's critical path (target encoder -> here -> decoder): its two independent MLPs run
-        # side by side (the scale MLP on branch lane 1; autograd replays the same split in the backward pass)
-        with ops.branch(lane=1):
-            scale = self.scale(h)
-        loc = self.location(h)
-        ops.join_branch(scale, lane=1)
-        return Normal(loc, scale), h
+        # q(z|x,y,v) sits on the step's critical path (target encoder -> here -> decoder): h = [hx ; hy ; v]
+        # (Models.py:911) is consumed in place by the row-MLP kernel, location and scale heads share each launch
+        loc, scale = ops.row_mlp([hx, hy, v], _mlp_heads(self.location, self.scale), (ops.ACT_NONE, ops.ACT_SOFTPLUS))
+        return Normal(loc, scale), _LazyCat((hx, hy, v))
 
 
 class ImageGlobalInferenceNetwork(GlobalInferenceNetwork):
@@ -96,6 +112,6 @@ class ImageGlobalInferenceNetwork(GlobalInferenceNetwork):
 
     def forward(self, z, x=None, x_lengths=None):
         gated = ops.gate(z, self.gate_affine_transform.weight, self.gate_affine_transform.bias)
-        loc = self.location(gated)
+        (loc,) = ops.row_mlp([gated], _mlp_heads(self.location), (ops.ACT_NONE,))
         # the scale branch never reaches the loss (VILoss.py:321): evaluate it only on demand
         return Normal(loc, lambda: self.scale(gated.detach()).detach()), None

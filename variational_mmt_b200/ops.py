@@ -7,12 +7,50 @@ themselves -- the Functions return ``None`` for parameters -- which is what make
 all-reduce and the fused clip+Adam single launches over one contiguous buffer.
 """
 import ctypes as C
+import os
 
 import torch
 from torch.autograd import Function
 
 from . import _lib as L
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, ACT_SOFTPLUS, ACT_SIGMOID, fptr, ptr, stream
+
+# ---- arithmetic mode: host-side state turned into the per-call `flags` of the C ABI (include/vmmt.h VMMT_F_*); the
+# library itself has no global mode ---------------------------------------------------------------------------------
+_mode = {"gemm": 1 if os.environ.get("VMMT_GEMM") == "simt" else 0, "background": False, "invariant": False}
+
+
+def set_gemm_mode(mode):
+    """0 = tensor cores, TF32 operands (fp32 storage; default); 1 = exact-fp32 SIMT contractions and recurrences
+    everywhere (parity debugging; also env VMMT_GEMM=simt); 2 = tensor cores, bf16 operands (the bf16 variant)."""
+    assert mode in (0, 1, 2)
+    _mode["gemm"] = int(mode)
+
+
+def get_gemm_mode():
+    return _mode["gemm"]
+
+
+def flags():
+    m = _mode["gemm"]
+    return (L.F_EXACT if m == 1 else L.F_BF16 if m == 2 else 0) | (L.F_BACKGROUND if _mode["background"] else 0) | \
+        (L.F_NO_SPLITK if _mode["invariant"] else 0)
+
+
+class batch_invariant(object):
+    """``with ops.batch_invariant():`` every contraction inside keeps one accumulation chain per output element in fixed K
+    order (no split-K): a row's result does not depend on how many rows share the call.  Used by the decoder
+    (translate/): a sentence decoded alone and the same sentence decoded in a batch give identical tokens."""
+
+    def __enter__(self):
+        self.prev = _mode["invariant"]
+        _mode["invariant"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _mode["invariant"] = self.prev
+        return False
+
 
 _seed_state = {"seed": 0x5EED, "offset": 0, "base": None}
 RNG_STEP_STRIDE = 1 << 16          # Philox offsets reserved per step (>> dropout / sample calls in one step)
@@ -125,13 +163,13 @@ class _OnSide(object):
                 pass                                   # not inside a backward pass: the caller joins explicitly
         self.ctx = torch.cuda.stream(side)
         self.ctx.__enter__()
-        L.lib.vmmt_gemm_set_background(1)
+        _mode["background"] = True
         _side["dirty"] = True
         return self
 
     def __exit__(self, *exc):
         if self.active:
-            L.lib.vmmt_gemm_set_background(0)
+            _mode["background"] = False
             self.ctx.__exit__(*exc)
         return False
 
@@ -239,7 +277,7 @@ def gemm(a, b, out, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NO
     """out[M,N] = act(op(a) op(b) + bias) (+out).  a, b, out: 2-D views with unit inner stride."""
     assert a.stride(-1) == 1 and b.stride(-1) == 1 and out.stride(-1) == 1
     L.call("vmmt_gemm", fptr(a), a.stride(0), int(a_kmajor), fptr(b), b.stride(0), int(b_kmajor),
-           fptr(out), out.stride(0), M, N, K, fptr(bias), act, int(accumulate), stream())
+           fptr(out), out.stride(0), M, N, K, fptr(bias), act, int(accumulate), flags(), stream())
     return out
 
 
@@ -247,7 +285,7 @@ def gemm_dual(a1, b1, a2, b2, out, M, N, K1, K2, bias=None, act=ACT_NONE):
     """out[M,N] = act(a1 b1^T + a2 b2^T + bias) in one launch (all operands [rows, K] with unit inner stride)."""
     assert a1.stride(-1) == 1 and b1.stride(-1) == 1 and a2.stride(-1) == 1 and b2.stride(-1) == 1 and out.stride(-1) == 1
     L.call("vmmt_gemm_dual", fptr(a1), a1.stride(0), fptr(b1), b1.stride(0), K1, fptr(a2), a2.stride(0), fptr(b2),
-           b2.stride(0), K2, fptr(out), out.stride(0), M, N, fptr(bias), act, stream())
+           b2.stride(0), K2, fptr(out), out.stride(0), M, N, fptr(bias), act, flags(), stream())
     return out
 
 
@@ -288,7 +326,7 @@ class LinearFn(Function):
     """y = act(x W[:, c0:c1]^T + b), optionally y = act(x W^T + b + addend) (nn.Linear + activation)."""
 
     @staticmethod
-    def forward(ctx, anchor, x, weight, bias, act, cols, addend):
+    def forward(ctx, anchor, x, weight, bias, act, cols, addend, rowwise=False):
         weight, bias = weight.t, bias.t
         x2 = x.reshape(-1, x.shape[-1])
         if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < x2.shape[1]):
@@ -296,7 +334,12 @@ class LinearFn(Function):
         c0, c1 = cols if cols is not None else (0, weight.shape[1])
         wv = weight[:, c0:c1]
         M, K, N = x2.shape[0], c1 - c0, weight.shape[0]
-        if addend is not None:
+        if rowwise:
+            # batch-row operand (one row per example): exact fp32, the same arithmetic per row whatever M is (csrc/rowlin.cu)
+            assert addend is None
+            y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+            rowlin([_rl_prob([x2], wv, bias, y, act)], M, N, K)
+        elif addend is not None:
             y = addend.reshape(M, N).clone()
             gemm(x2, wv, y, M, N, K, bias=bias, act=act, accumulate=2)
         else:
@@ -331,7 +374,7 @@ class LinearFn(Function):
             if bias is not None and bias.requires_grad:
                 colsum_acc(dpre, M, N, grad_buf(bias))
         dadd = dpre.view(*ctx.xshape[:-1], N) if ctx.has_addend and ctx.needs_input_grad[6] else None
-        return None, dx, None, None, None, None, dadd
+        return None, dx, None, None, None, None, dadd, None
 
 
 class DualLinearFn(Function):
@@ -386,8 +429,121 @@ def dual_linear(x1, x2, weight, act=ACT_NONE):
     return DualLinearFn.apply(_anchor(x1.device), x1, x2, _P(weight), act)
 
 
-def linear(x, weight, bias=None, act=ACT_NONE, cols=None, addend=None):
-    return LinearFn.apply(_anchor(x.device), x, _P(weight), _P(bias), act, cols, addend)
+def linear(x, weight, bias=None, act=ACT_NONE, cols=None, addend=None, rowwise=False):
+    """``rowwise``: x has one row per example (z, pooled encodings): exact-fp32 row kernel instead of the tensor-core GEMM."""
+    return LinearFn.apply(_anchor(x.device), x, _P(weight), _P(bias), act, cols, addend, rowwise)
+
+
+# --------------------------------------------------------------------------------------------
+def _rl_prob(xsegs, w, bias, out, act=ACT_NONE, y=None, yact=ACT_NONE, xt_out=None):
+    """One VmmtRowLin problem: x = [xsegs...] column-wise, forward (w [N,K]) or gradient (w [K,N]) form."""
+    q = L.RowLin()
+    k0 = 0
+    assert 1 <= len(xsegs) <= 3
+    for i, t in enumerate(xsegs):
+        assert t.dim() == 2 and t.stride(1) == 1
+        q.seg[i].p, q.seg[i].ld, q.seg[i].k0 = fptr(t), t.stride(0), k0
+        k0 += t.shape[1]
+    q.nseg, q.act = len(xsegs), act
+    q.y, q.ldy, q.yact = fptr(y), (y.stride(0) if y is not None else 0), yact
+    q.w, q.ldw, q.bias = fptr(w), w.stride(0), fptr(bias)
+    q.out, q.ldo = fptr(out), out.stride(0)
+    q.xt_out, q.ld_xt = fptr(xt_out), (xt_out.stride(0) if xt_out is not None else 0)
+    return q
+
+
+def rowlin(probs, M, N, K, sum_outputs=False, transposed=False):
+    arr = (L.RowLin * len(probs))(*probs)
+    L.call("vmmt_rowlin", arr, len(probs), int(sum_outputs), int(transposed), M, N, K, stream())
+
+
+class RowMLPFn(Function):
+    """One or two 2-layer MLP heads over the same batch rows, exact fp32 (csrc/rowlin.cu):
+    y_p = act_p(relu(x W1_p^T + b1_p) W2_p^T + b2_p) -- LocationLayer / ScaleLayer pairs of the prior, posterior and image
+    networks (onmt/modules/NormalVariationalEncoder.py:12-43).  x = [xsegs...] column-wise, never materialised.
+
+    forward(anchor, params = _P((W1, b1, W2, b2) per head), acts, *xsegs) -> y_0 [, y_1]
+    Two launches forward (layer 1 of all heads, layer 2 of all heads), two backward on the critical path (input
+    gradients); weight / bias gradients go to the side stream through the tensor-core GEMM."""
+
+    @staticmethod
+    def forward(ctx, anchor, params, acts, *xsegs):
+        heads = params.t
+        nh = len(heads)
+        xs = [x if (x.stride(1) == 1) else x.contiguous() for x in xsegs]
+        M = xs[0].shape[0]
+        K = sum(x.shape[1] for x in xs)
+        N1, N2 = heads[0][0].shape[0], heads[0][2].shape[0]
+        for W1, b1, W2, b2 in heads:
+            assert W1.shape == (N1, K) and W2.shape == (N2, N1)
+        dev = xs[0].device
+        hs = [torch.empty(M, N1, device=dev, dtype=torch.float32) for _ in range(nh)]
+        ys = [torch.empty(M, N2, device=dev, dtype=torch.float32) for _ in range(nh)]
+        rowlin([_rl_prob(xs, W1, b1, h, ACT_RELU) for (W1, b1, _, _), h in zip(heads, hs)], M, N1, K)
+        rowlin([_rl_prob([h], W2, b2, y, a) for (_, _, W2, b2), h, y, a in zip(heads, hs, ys, acts)], M, N2, N1)
+        ctx.save_for_backward(*xs, *hs, *ys)
+        ctx.heads, ctx.acts, ctx.nx = heads, acts, len(xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        heads, acts, nx = ctx.heads, ctx.acts, ctx.nx
+        nh = len(heads)
+        saved = ctx.saved_tensors
+        xs, hs, ys = saved[:nx], saved[nx:nx + nh], saved[nx + nh:]
+        M = xs[0].shape[0]
+        K = sum(x.shape[1] for x in xs)
+        N1, N2 = heads[0][0].shape[0], heads[0][2].shape[0]
+        dev = xs[0].device
+        dys = [torch.zeros_like(y) if d is None else d.contiguous() for d, y in zip(dys, ys)]
+        # layer 2: dh_p = (dy_p * act'(y_p)) W2_p; the transformed dy_p (= d pre-activation) is kept for dW2 / db2
+        dpre2 = [torch.empty(M, N2, device=dev, dtype=torch.float32) for _ in range(nh)]
+        dhs = [torch.empty(M, N1, device=dev, dtype=torch.float32) for _ in range(nh)]
+        rowlin([_rl_prob([dy], W2, None, dh, y=(y if a != ACT_NONE else None), yact=a, xt_out=dp)
+                for (_, _, W2, _), dy, dh, y, a, dp in zip(heads, dys, dhs, ys, acts, dpre2)],
+               M, N1, N2, transposed=True)
+        # layer 1: dx = sum_p (dh_p * relu'(h_p)) W1_p over the column range some input needs
+        need = [bool(ctx.needs_input_grad[3 + i]) for i in range(nx)]
+        dpre1 = [torch.empty(M, N1, device=dev, dtype=torch.float32) for _ in range(nh)]
+        dxs = [None] * nx
+        if any(need):
+            offs = [0]
+            for x in xs:
+                offs.append(offs[-1] + x.shape[1])
+            c0 = min(offs[i] for i in range(nx) if need[i])
+            c1 = max(offs[i + 1] for i in range(nx) if need[i])
+            dx = torch.empty(M, c1 - c0, device=dev, dtype=torch.float32)
+            rowlin([_rl_prob([dh], W1[:, c0:c1], None, dx, y=h, yact=ACT_RELU, xt_out=dp)
+                    for (W1, _, _, _), dh, h, dp in zip(heads, dhs, hs, dpre1)],
+                   M, c1 - c0, N1, sum_outputs=(nh == 2), transposed=True)
+            for i in range(nx):
+                if need[i]:
+                    dxs[i] = dx[:, offs[i] - c0: offs[i + 1] - c0]
+        else:
+            for dh, h, dp in zip(dhs, hs, dpre1):
+                L.call("vmmt_act_bwd", fptr(dh), fptr(h), fptr(dp), dh.numel(), ACT_RELU, stream())
+        with on_side(*dpre1, *dpre2, *hs, *xs):                               # they only feed the optimiser
+            for (W1, b1, W2, b2), h, d1, d2 in zip(heads, hs, dpre1, dpre2):
+                if W2.requires_grad:
+                    gemm(d2, h, grad_buf(W2), N2, N1, M, a_kmajor=False, b_kmajor=False, accumulate=1)
+                if b2 is not None and b2.requires_grad:
+                    colsum_acc(d2, M, N2, grad_buf(b2))
+                if W1.requires_grad:
+                    k0 = 0
+                    for x in xs:
+                        gemm(d1, x, grad_buf(W1)[:, k0:k0 + x.shape[1]], N1, x.shape[1], M, a_kmajor=False,
+                             b_kmajor=False, accumulate=1)
+                        k0 += x.shape[1]
+                if b1 is not None and b1.requires_grad:
+                    colsum_acc(d1, M, N1, grad_buf(b1))
+        return (None, None, None, *dxs)
+
+
+def row_mlp(xsegs, heads, acts):
+    """heads: [(W1, b1, W2, b2), ...] (1 or 2), acts: output activation per head -> tuple of outputs."""
+    xsegs = [x.reshape(-1, x.shape[-1]) for x in xsegs]
+    return RowMLPFn.apply(_anchor(xsegs[0].device), _P(tuple(tuple(h) for h in heads)), tuple(acts), *xsegs)
+
 
 
 # --------------------------------------------------------------------------------------------
@@ -444,9 +600,8 @@ class LSTMLayerFn(Function):
             D.reverse = 1 if d == 1 else 0
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
-        L.lib.vmmt_lstm_set_cluster_budget(int(cfg.get("cluster_budget") or 0))
-        L.call("vmmt_lstm_seq_fwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
-        L.lib.vmmt_lstm_set_cluster_budget(0)
+        L.call("vmmt_lstm_seq_fwd", dirs, ndir, ptr(lengths), T, N, Hd, flags(), int(cfg.get("cluster_budget") or 0),
+               fptr(ws), ws_bytes, stream())
         if save:
             ctx.save_for_backward(None if gx_given else x, out, gates, cs, h0, c0, rowbias, lengths)
             ctx.weights, ctx.cfg = weights, (ndir, T, N, In, Hd, c0c, c1c)
@@ -490,9 +645,8 @@ class LSTMLayerFn(Function):
             D.reverse = 1 if d == 1 else 0
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
-        L.lib.vmmt_lstm_set_cluster_budget(ctx.cluster_budget)
-        L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, fptr(ws), ws_bytes, stream())
-        L.lib.vmmt_lstm_set_cluster_budget(0)
+        L.call("vmmt_lstm_seq_bwd", dirs, ndir, ptr(lengths), T, N, Hd, flags(), ctx.cluster_budget, fptr(ws), ws_bytes,
+               stream())
         if early_ev is not None:
             _fire_early_exchange(early_ev)
         x2 = x.view(T * N, In) if not gx_given else None
@@ -719,7 +873,7 @@ class VILossFn(Function):
             L.call("vmmt_kl_fwd", fptr(mu_q), fptr(sd_q), fptr(mu_p), fptr(sd_p), fptr(stats[3:4]), B, Z, stream())
             L.call("vmmt_image_loss_fwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(stats[4:6]), B, D, stream())
         L.call("vmmt_generator_nll_fwd", fptr(out2d), fptr(gen_w), fptr(gen_b), ptr(target), cfg["pad_idx"],
-               M, H, V, fptr(lse), fptr(stats[0:3]), fptr(ws), wsb, stream())
+               M, H, V, fptr(lse), fptr(stats[0:3]), fptr(ws), wsb, flags(), stream())
         cur.wait_stream(_loss_stream)
         kw = float(cfg["kl_weight"])
         loss = torch.empty(1, device=dev, dtype=torch.float32)
@@ -759,10 +913,10 @@ class VILossFn(Function):
         wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
         L.call("vmmt_generator_nll_bwd", fptr(out2d), fptr(ctx.gen_w), fptr(ctx.gen_b), ptr(target),
-               cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), None, None, fptr(ws), wsb, stream())
+               cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), None, None, fptr(ws), wsb, flags(), stream())
         with on_side(ws, out2d):                               # generator weight gradient: off the critical path
             L.call("vmmt_generator_nll_wgrad", fptr(out2d), fptr(ws), M, H, V, fptr(grad_buf(ctx.gen_w)),
-                   fptr(grad_buf(ctx.gen_b)), stream())
+                   fptr(grad_buf(ctx.gen_b)), flags(), stream())
         cur.wait_stream(_loss_stream)
         return dx, None, None, None, dmq, dsq, dmp, dsp, dloc, None, None
 
@@ -778,5 +932,5 @@ def generator_logprobs(x2d, weight, bias):
     V = weight.shape[0]
     out = torch.empty(M, V, device=x2d.device, dtype=torch.float32)
     lse = torch.empty(M, device=x2d.device, dtype=torch.float32)
-    L.call("vmmt_generator_logprobs", fptr(x2d), fptr(weight), fptr(bias), M, H, V, fptr(out), fptr(lse), stream())
+    L.call("vmmt_generator_logprobs", fptr(x2d), fptr(weight), fptr(bias), M, H, V, fptr(out), fptr(lse), flags(), stream())
     return out

@@ -59,7 +59,9 @@ class TranslatorMultimodalVI(object):
     # ------------------------------------------------------------------------------------------
     def _buffers(self, B, S, dev):
         """Static device buffers (and the captured step graph) of one (sentences, src_len) bucket."""
-        key = (B, S, str(dev), int(L.lib.vmmt_get_gemm_mode()))
+        # the captured step graph bakes in raw parameter addresses: they are part of the key (Optim.set_parameters re-homes
+        # the flat buffers into the NVLink peer segment, model.to() re-flattens them -- a stale bucket must not be replayed)
+        key = (B, S, str(dev), ops.flags(), next(self.model.parameters()).data_ptr())
         st = self._buckets.get(key)
         if st is not None:
             self._buckets.move_to_end(key)
@@ -95,7 +97,8 @@ class TranslatorMultimodalVI(object):
         st.qp, st.cvec, st.out = (torch.zeros(R, H, **f32) for _ in range(3))
         # generator: with the tensor-core GEMM the epilogue keeps per-tile {max, sum exp, top-K} only; the [R,V] log-prob
         # matrix exists only on the exact-fp32 (SIMT) parity path
-        st.fused_gen = bool(L.lib.vmmt_generator_topk_supported(fptr(st.out), fptr(model.generator[0].weight), R, H, V))
+        st.fused_gen = bool(L.lib.vmmt_generator_topk_supported(fptr(st.out), fptr(model.generator[0].weight), R, H, V,
+                                                              ops.flags()))
         if st.fused_gen:
             st.gen_ws_bytes = int(L.lib.vmmt_generator_topk_workspace_bytes(R, V, K))
             st.gen_ws = torch.zeros(st.gen_ws_bytes // 4, **f32)
@@ -154,13 +157,13 @@ class TranslatorMultimodalVI(object):
         # generator + Beam.advance for every sentence + DecoderState.beam_update (Beam.py:64-123, Models.py:589-594)
         if st.fused_gen:
             L.call("vmmt_generator_topk", fptr(st.out), fptr(gen.weight), fptr(gen.bias), R, H, V, K, fptr(st.gen_ws),
-                   st.gen_ws_bytes, sm)
+                   st.gen_ws_bytes, ops.flags(), sm)
             L.call("vmmt_beam_advance_topk", fptr(st.gen_ws), B, K, V, 0, ptr(st.step), ptr(st.tok_cur),
                    ptr(st.prev_cur), self.eos, fptr(st.scores), ptr(st.next_ys), ptr(st.prev_ks), fptr(st.fin_score),
                    ptr(st.fin_t), ptr(st.fin_k), ptr(st.n_fin), ptr(st.done), ptr(st.n_active), sm)
         else:
             L.call("vmmt_generator_logprobs", fptr(st.out), fptr(gen.weight), fptr(gen.bias), R, H, V, fptr(st.logp),
-                   fptr(st.lse), sm)
+                   fptr(st.lse), ops.flags(), sm)
             L.call("vmmt_beam_advance", fptr(st.logp), B, K, V, 0, ptr(st.step), ptr(st.tok_cur), ptr(st.prev_cur),
                    self.eos, fptr(st.scores), ptr(st.next_ys), ptr(st.prev_ks), fptr(st.fin_score), ptr(st.fin_t),
                    ptr(st.fin_k), ptr(st.n_fin), ptr(st.done), ptr(st.n_active), sm)
@@ -182,6 +185,12 @@ class TranslatorMultimodalVI(object):
 
     @torch.no_grad()
     def translate_batch(self, batch, data=None, sent_idx=None):
+        # batch-invariant arithmetic: a sentence decoded alone = the same sentence decoded inside a batch (the reference
+        # decodes one sentence at a time, translate_mm_vi.py:80-82; batching must not change its output)
+        with ops.batch_invariant():
+            return self._translate_batch(batch, data, sent_idx)
+
+    def _translate_batch(self, batch, data=None, sent_idx=None):
         model = self.model
         dec = model.decoder
         assert not model.training, "call model.eval() before translating"
@@ -212,7 +221,8 @@ class TranslatorMultimodalVI(object):
         st.c.view(nl, K, B, H).copy_(c0.unsqueeze(1).expand(nl, K, B, H))
         E = dec.embeddings.embedding_size
         zb = torch.empty(B, 4 * H, device=dev)
-        ops.gemm(z.contiguous(), dec.rnn.weight_ih_l0[:, E:], zb, B, 4 * H, z.size(1))   # z W_ih[:, E:]^T once per batch
+        # z W_ih[:, E:]^T once per batch, exact fp32 per row (as the training path: VI_Model1.StdRNNVIModel1Decoder)
+        ops.rowlin([ops._rl_prob([z.contiguous()], dec.rnn.weight_ih_l0[:, E:], None, zb)], B, 4 * H, z.size(1))
         st.zb.view(K, B, 4 * H).copy_(zb.unsqueeze(0).expand(K, B, 4 * H))
         self._reset(st)
         Lmax = self.max_length
