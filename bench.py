@@ -2,7 +2,7 @@
 """bench.py -- training target-tokens/s of the VI-model-1 step (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload cfg1|cfg1_ragged|cfg5|decode] [--dtype fp32] [--profile-calls]
+                    [--workload cfg1|cfg1_ragged|cfg5|decode] [--dtype f32|bf16]
 
 One "step" = one optimiser update of the conditional VI model 1 on one synthetic Multi30k-shaped
 batch per rank: NMTVIModel.forward -> NMTVIModel1LossCompute.
@@ -15,7 +15,16 @@ in-kernel Philox latent noise are ON (training configuration of run_translated_m
   e2e   : same metric through the public module API with HOST (pinned) buffers: every step copies
           that step's ids / lengths / image features host->device and reads the loss statistics
           device->host inside the timed region.
-  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+  roofline : the kernel with the LARGEST time share of the step (the LSTM recurrence, profiles/launches_r2_summary.txt),
+          timed alone with CUDA events: algorithmic FLOP/s against the measured tensor peak, us per recurrence step against
+          a measured synchronisation floor (the same kernel with the MMAs and transcendentals removed).
+          roofline_step = algorithmic FLOPs of the whole step / step time / peak; roofline_others: generator GEMM, clip+Adam,
+          attention core against their rooflines.
+  dp_parity (N > 1): one un-timed step checked before the timed region: replicas bit-identical, two-phase = one-phase = NCCL
+          exchange, N-rank step = rank 0's accumulation over the same N batches (the reference's -accum_count N).
+  gpu_torch_baseline (N = 1, informational): the oracle port on the same GPU through torch's cuDNN LSTM + cuBLAS.
+  decode (N = 1): beam-5 decode sentences/s of a short run (BASELINE metric's second half; --workload decode is the full one).
+  cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
 
 `--impl reference` times the CPU path (the oracle port of the reference step -- the reference itself
 is a Python package that lives in /root/reference and does not travel to the GPU box) on the host
@@ -121,6 +130,12 @@ def _gpu_index_for_nvml(local_rank):
     return local_rank
 
 
+def _config(workload, desc, global_batch, tokens_per_step, params, gemm, parallelism, exchange, launch, l2):
+    """The config block of the JSON line: the SAME keys on both arms (the driver compares them)."""
+    return {"workload": workload, "desc": desc, "global_batch": global_batch, "tokens_per_step": tokens_per_step,
+            "params": params, "gemm": gemm, "parallelism": parallelism, "exchange": exchange, "launch": launch, "l2": l2}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     """CPU arm: the oracle port of the reference training step on the host cores (rank 0 only)."""
@@ -139,8 +154,9 @@ def run_reference(args):
         "unit": "tokens/s", "n_gpus": args.gpus, "steps": res["steps"], "warmup": res["warmup"],
         "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": desc, "global_batch": bk["batch_size"],
-                   "tokens_per_step": res["tokens_per_step"]},
+        "config": _config(args.workload, desc, bk["batch_size"], res["tokens_per_step"], cpu_baseline.synth.num_params(
+            cpu_baseline._cfg_of(mk)), "fp32 (torch CPU, oneDNN)", "none (one process on the host cores)", "none",
+            "eager torch on the host", "n/a (host)"),
         "cpu_baseline": {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"],
                          "kind": "port", "sample": res["sample"]},
         "e2e": {"value": res["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0,
@@ -178,6 +194,8 @@ def run_ours(args):
 
     mk, bk, desc = WORKLOADS[args.workload]
     B = bk["batch_size"]
+    if args.dtype == "bf16":
+        ops.set_gemm_mode(2)                              # bf16 tensor-core operands, fp32 accumulate / state / master weights
     opt = synthetic.make_opt(emb=mk["emb"], hidden=mk["hidden"], z_dim=mk["z"], conditional=mk["conditional"],
                              dropout=0.5)
     fields = synthetic.make_fields(mk["v"], mk["v"])
@@ -269,6 +287,15 @@ def run_ours(args):
             return float(mx[0]), float(mx[1]), float(sm[2])
         return float(t[0]), float(t[1]), float(t[2])
 
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        try:
+            dp_parity = check_dp_parity(vm, ops, synthetic, mk, bk, opt, fields, shard, dev, rank, world, optim, model, loss_fn)
+        except Exception as e:                            # noqa: BLE001  (reported, never fatal to the measurement)
+            dp_parity = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
+        vm.manual_seed(3435 + rank)                       # the check re-seeded the Philox streams
+        barrier()
+
     # warm-up (also sizes the caching allocator)
     for i in range(max(args.warmup, 3)):
         step(resident[i % NB], False)
@@ -306,61 +333,86 @@ def run_ours(args):
     cpu_b = None
     if rank == 0:
         peaks, how = _peaks()
-        roof = roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev)
+        tf32_peak = peaks["bf16_tflops"] / 2.0
+        tc_peak = peaks["bf16_tflops"] if args.dtype == "bf16" else tf32_peak
+        gen_roof = roofline_generator(args, mk, bk, shard, model, peaks, how, vm, _lib, dev)
+        S_src = int(resident[0][0].size(0))
+        roof = roofline_lstm(mk, B, S_src, peaks, how, ops, _lib, dev)
+        # whole step: algorithmic FLOPs (SURVEY 8d formulas, 3x forward) against the tensor peak of the operand type
+        Td = int(resident[0][2].size(0)) - 1
+        flops = step_flops(mk, B, S_src, Td, min(Td, shard))
+        step_s = dev_ms / args.steps / 1e3
+        roof_step = {"flops_per_step": flops, "achieved": flops / step_s / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                     "frac": flops / step_s / 1e12 / tc_peak,
+                     "note": "3 x forward FLOPs of SURVEY.md 8(d); the step is a chain of ~200 sequential recurrence steps at "
+                             "batch %d: latency-bound, not tensor-bound" % B}
         if n_gpus == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline
             cores = os.cpu_count() or 1
             r = cpu_baseline.time_train_steps(mk, bk, steps=2, warmup=1, threads=cores, budget_s=args.cpu_budget)
             cpu_b = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "port",
                      "sample": r["sample"]}
+        gpu_torch = None
+        if n_gpus == 1 and not args.no_cpu_baseline and args.workload != "cfg5":
+            try:                                          # informational yardstick: the library path (cuDNN + cuBLAS) on this GPU
+                from oracle import cpu_baseline
+                r = cpu_baseline.time_train_steps(mk, bk, steps=20, warmup=5, budget_s=10.0, device=str(dev))
+                gpu_torch = {"value": r["tokens_per_s"], "unit": "tokens/s", "ms_per_step": r["ms_per_step"],
+                             "kind": "oracle port on cuda (torch eager: cuDNN LSTM + cuBLAS)", "sample": r["sample"]}
+            except Exception as e:                        # noqa: BLE001
+                gpu_torch = {"error": "%s: %s" % (type(e).__name__, e)}
+        decode_line = None
+        if n_gpus == 1 and args.workload == "cfg1" and not args.no_decode:
+            try:
+                decode_line = short_decode(vm, synthetic, mk, dev)
+            except Exception as e:                        # noqa: BLE001
+                decode_line = {"error": "%s: %s" % (type(e).__name__, e)}
         # other entry points against their rooflines, from the per-call device times of the profiled eager step
-        others = {}
+        others = {"generator fwd GEMM + LSE epilogue": gen_roof}
         pc = dict(per_call)
-        H_, S_ = mk["hidden"], int(resident[0][0].size(0))
+        H_, S_ = mk["hidden"], S_src
         if "vmmt_adam_clip_step" in pc and "vmmt_sqnorm" in pc:
             t = (pc["vmmt_adam_clip_step"][1] + pc["vmmt_sqnorm"][1]) * 1e-3
             gbs = 32.0 * n_params / t / 1e9      # sqnorm reads g (4 B), Adam reads p,g,m,v and writes p,m,v (28 B)
             others["clip+adam (vmmt_sqnorm + vmmt_adam_clip_step)"] = {
                 "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                 "bytes": "32 B/param"}
-        if "vmmt_lstm_seq_fwd" in pc:
-            cnt, tot = pc["vmmt_lstm_seq_fwd"]
-            others["lstm recurrence fwd (vmmt_lstm_seq_fwd, %d launches)" % cnt] = {
-                "bound": "latency", "us_per_launch": 1e3 * tot / cnt,
-                "note": "sequential dependence: ~30 steps x (32 tcgen05.mma + cell update + DSMEM hand-off) per launch; "
-                        "neither the HBM nor the tensor roofline applies (8*N*H^2 = %.2f GFLOP per step)" % (8.0 * B * H_ * H_ / 1e9)}
-        if "vmmt_lstm_seq_bwd" in pc:
-            cnt, tot = pc["vmmt_lstm_seq_bwd"]
-            others["lstm recurrence bwd (vmmt_lstm_seq_bwd, %d launches)" % cnt] = {"bound": "latency", "us_per_launch": 1e3 * tot / cnt}
         if "vmmt_attention_fwd" in pc:
             cnt, tot = pc["vmmt_attention_fwd"]
-            Td = int(resident[0][2].size(0)) - 1
             byts = 4.0 * (2 * B * Td * H_ + B * S_ * H_ + B * Td * S_)
             gbs = byts * cnt / (tot * 1e-3) / 1e9
             others["attention core fwd (vmmt_attention_fwd)"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                                                  "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                                                                  "bytes": "4*(2*B*T*H + B*S*H + B*T*S)"}
+        if "vmmt_rowlin" in pc:
+            cnt, tot = pc["vmmt_rowlin"]
+            others["batch-row MLPs (vmmt_rowlin, %d launches)" % cnt] = {
+                "bound": "hbm", "us_total": 1e3 * tot, "note": "exact-fp32 cluster split-K; weights streamed once per launch"}
         line = {
             "metric": "train_target_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": args.workload, "desc": desc, "global_batch": B * n_gpus,
-                       "tokens_per_step": tok / args.steps, "params": n_params,
-                       "gemm": "tf32 tcgen05 (fp32 storage, fp32 accumulate)" if ops.get_gemm_mode() == 0
-                               else "fp32 simt",
-                       "parallelism": "dp%d" % n_gpus,
-                       "exchange": optim.exchange_in_use,
-                       "launch": "eager" if graphed is None else "cuda graph (fwd+loss+bwd) + eager gradient exchange/clip/Adam",
-                       "l2": "no flush: each step streams params+grads+Adam moments (%.0f MB) > 126 MB L2 and "
-                             "rotates over %d different batches" % (16.0 * n_params / 1e6, NB)},
+            "config": _config(
+                args.workload, desc, B * n_gpus, tok / args.steps, n_params,
+                {0: "tf32 tcgen05 GEMMs + fp16-operand tcgen05 recurrence, exact-fp32 batch-row networks (fp32 storage, fp32 accumulate)",
+                 1: "fp32 simt", 2: "bf16 tcgen05 GEMMs + fp16-operand recurrence (fp32 master weights, accumulate, state)"}[
+                    ops.get_gemm_mode()],
+                "dp%d" % n_gpus, optim.exchange_in_use,
+                "eager" if graphed is None else "cuda graph (fwd+loss+bwd) + eager gradient exchange/clip/Adam",
+                "no flush: each step streams params+grads+Adam moments (%.0f MB) > 126 MB L2 and rotates over %d different "
+                "batches" % (16.0 * n_params / 1e6, NB)),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 32, "ms_per_step": max(e2e_wall, e2e_ms) / args.steps},
             "host_wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "roofline_step": roof_step,
             "cpu_baseline": cpu_b,
+            "gpu_torch_baseline": gpu_torch,
+            "decode": decode_line,
+            "dp_parity": dp_parity,
             "top_calls_ms": {k: round(v[1], 3) for k, v in top[:8]},
             "roofline_others": others,
         }
@@ -526,10 +578,215 @@ def run_decode(args):
     return 0
 
 
-def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
-    """Times the dominant kernel of the step (the fused generator+NLL forward GEMM) in isolation with
-    CUDA events on the launching stream and reports it against the measured tensor peak.  DESIGN.md
-    ("Measurement") states the algorithmic FLOPs."""
+def step_flops(mk, B, S, T, Tscored):
+    """Algorithmic FLOPs of one training step = 3 x forward: LSTM stacks, attention, generator, latent
+    and image networks (the dead scale branch of the image head is not counted: it is not computed)."""
+    E, H, Z, V, D = mk["emb"], mk["hidden"], mk["z"], mk["v"], 2048
+    enc = 8.0 * B * S * H * (E + 3 * H)
+    dec = 8.0 * B * T * H * (E + Z + 3 * H)
+    tgt = 8.0 * B * (T + 1) * H * (E + 2 * H) if mk["conditional"] else 0.0
+    attn = B * T * (6.0 * H * H + 4.0 * S * H)
+    gen = 2.0 * B * Tscored * H * V
+    lat = 2.0 * B * 2 * (H * Z + Z * Z) + (2.0 * B * 2 * ((2 * H + D) * Z + Z * Z) if mk["conditional"] else 0.0)
+    img = B * (2.0 * Z + 2.0 * (Z * D + D * D))
+    return 3.0 * (enc + dec + tgt + attn + gen + lat + img)
+
+
+def roofline_lstm(mk, B, S, peaks, how, ops, _lib, dev):
+    """The kernel pair with the largest time share of the step (profiles/launches_r2_summary.txt): the cluster-resident
+    LSTM recurrence, forward + BPTT, of ONE layer of the source encoder (T = S, N = B, H = hidden), timed alone with CUDA
+    events on the launching stream (median of 10, inputs rotated through a buffer larger than L2 is unnecessary: the layer
+    re-reads 28 MB of W_hh slices per launch through L2 by design).  Reported three ways:
+      * achieved / peak: algorithmic FLOPs 16 N H^2 T (forward h W_hh^T + backward dG W_hh) over the measured fp16/bf16
+        tensor peak -- the contract's number; it is tiny because the recurrence is a dependency chain, not a GEMM;
+      * us_per_step: the kernel's time per recurrence step;
+      * floor_us_per_step: the SAME kernel with one k-block of MMAs and no transcendentals (env VMMT_LSTM_FLOOR): what the
+        per-step synchronisation (DSMEM hand-off, mbarriers, tcgen05.ld, gate exchange) costs by itself."""
+    import torch
+    H, T, N = mk["hidden"], S, B
+    if H > 512:
+        return {"kernel": "lstm step-wise path (H > 512): see roofline_others", "bound": "tensor", "achieved": None, "peak": None,
+                "unit": "TFLOP/s", "frac": None, "traffic": None}
+    x = (torch.randn(T, N, mk["emb"], device=dev) * 0.5).requires_grad_(True)
+    ws = [(torch.randn(4 * H, mk["emb"], device=dev) * 0.1).requires_grad_(True), (torch.randn(4 * H, H, device=dev) * 0.1).requires_grad_(True),
+          (torch.randn(4 * H, device=dev) * 0.1).requires_grad_(True), (torch.randn(4 * H, device=dev) * 0.1).requires_grad_(True)]
+
+    def run():
+        prof = []
+        _lib.set_profile(prof)
+        o, hT, cT = ops.lstm_layer(x, None, None, None, None, {"save": True}, ws)
+        o.sum().backward()
+        torch.cuda.synchronize()
+        _lib.set_profile(None)
+        return {n: e0.elapsed_time(e1) for n, a, e0, e1 in prof if "lstm_seq" in n}
+
+    def med(env):
+        if env:
+            os.environ["VMMT_LSTM_FLOOR"] = "1"
+        try:
+            for _ in range(3):
+                run()
+            rs = [run() for _ in range(10)]
+        finally:
+            os.environ.pop("VMMT_LSTM_FLOOR", None)
+        f = sorted(r["vmmt_lstm_seq_fwd"] for r in rs)[5]
+        b = sorted(r["vmmt_lstm_seq_bwd"] for r in rs)[5]
+        return f, b
+    f_ms, b_ms = med(False)
+    ff_ms, fb_ms = med(True)
+    flops = 16.0 * N * H * H * T
+    ach = flops / ((f_ms + b_ms) * 1e-3) / 1e12
+    peak = peaks["bf16_tflops"]
+    return {"kernel": "lstm_tc_fwd_kernel + lstm_tc_bwd_kernel, one source-encoder layer (T=%d, N=%d, H=%d): largest time share "
+                      "of the step (12 such launches per step)" % (T, N, H),
+            "bound": "tensor", "limit": "latency: T sequential steps, each a cluster-wide h hand-off",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_flops": flops, "ms": f_ms + b_ms,
+            "us_per_step": {"fwd": 1e3 * f_ms / T, "bwd": 1e3 * b_ms / T},
+            "floor_us_per_step": {"fwd": 1e3 * ff_ms / T, "bwd": 1e3 * fb_ms / T},
+            "frac_of_floor": {"fwd": ff_ms / f_ms, "bwd": fb_ms / b_ms},
+            "peak_source": "%s bf16 burst %.0f TF/s (fp16 operands run at the bf16 rate)" % (how, peaks["bf16_tflops"])}
+
+
+def short_decode(vm, synthetic, mk, dev, n_batches=2, Bd=250):
+    """Secondary field of the default line: beam-5 decode sentences/s over `n_batches` batches of 250 sentences (after
+    the buckets' step graphs are captured); the full measurement is --workload decode."""
+    import numpy as np
+    import torch
+    opt = synthetic.make_opt(emb=mk["emb"], hidden=mk["hidden"], z_dim=mk["z"], conditional=True, dropout=0.5)
+    fields = synthetic.make_fields(mk["v"], mk["v"])
+    torch.manual_seed(3435)
+    model = vm.make_vi_model_mmt(opt, fields, gpu=True)
+    model.eval()
+    tr = vm.TranslatorMultimodalVI(model, fields, beam_size=5, n_best=1, max_length=100,
+                                   global_scorer=vm.GNMTGlobalScorer(0., -0.), cuda=True,
+                                   test_img_feats=np.zeros((1, 2048), np.float32), multimodal_model_type="vi-model1")
+
+    class Bt:
+        pass
+    bs = []
+    for i in range(2):
+        src, sl, _t, _tl, _img = synthetic.random_batch(mk["v"], mk["v"], Bd, 8, seed=5000 + i)
+        b = Bt(); b.batch_size = Bd; b.src = (src.to(dev), sl.to(dev))
+        bs.append(b)
+    for i in range(4):
+        tr.translate_batch(bs[i % 2], None, None)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(n_batches):
+        tr.translate_batch(bs[i % 2], None, None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    return {"metric": "beam_decode_sentences_per_sec", "value": n_batches * Bd / (ms / 1e3), "unit": "sentences/s",
+            "sentences": n_batches * Bd, "beam": 5, "max_length": 100, "ms_per_batch": ms / n_batches,
+            "note": "prior-only beam search, 250 sentences per batch; full run: bench.py --workload decode"}
+
+
+def check_dp_parity(vm, ops, synthetic, mk, bk, opt, fields, shard, dev, rank, world, optim_main, model_main, loss_main):
+    """One un-timed data-parallel step, checked three ways before anything is timed (reference semantics:
+    onmt/TrainerMultimodal.py:342-346,625-718, -accum_count N):
+      1. replicas: after the step every rank holds bit-identical parameters (checksums over the int32 view);
+      2. exchanges: the two-phase NVLink exchange (what is timed), the one-phase NVLink exchange and the NCCL all-reduce +
+         replicated clip/Adam give the same parameters up to summation-order round-off;
+      3. accumulation: rank 0 back-propagates all N batches into one gradient buffer (normalisation = global sentence
+         count), clips and steps alone: the N-rank step must equal it.
+    Eager launches, dropout 0.5 ON with per-rank Philox seeds re-seeded identically for every variant."""
+    import torch
+    import torch.distributed as dist
+    B = bk["batch_size"]
+    norm = B * world
+    host = [synthetic.random_batch(mk["v"], mk["v"], B, 2048, seed=77000 + r, full_length=bk.get("full_length"))
+            for r in range(world)]
+
+    class Bt:
+        pass
+
+    def fwd_bwd(model, loss_fn, r, zero=True):
+        src, sl, tgt, tl, img = [t.to(dev) for t in host[r]]
+        vm.manual_seed(4242 + r)                        # the rank's Philox stream, identical in every variant
+        ops.begin_step()
+        if zero:
+            model.zero_grad()
+        out, attns, _ = model(src.unsqueeze(2), tgt.unsqueeze(2), sl, tl, img)
+        b = Bt()
+        b.tgt, b.batch_size = tgt, B
+        loss_fn.sharded_compute_loss(b, out, attns, 0, tgt.size(0), shard, norm)
+
+    def fresh(exchange, early):
+        torch.manual_seed(3435)
+        m = vm.make_vi_model_mmt(opt, fields, gpu=True)
+        m.train()
+        lf = vm.NMTVIModel1LossCompute(m.generator, fields["tgt"].vocab)
+        o = vm.Optim("adam", 0.002, 5, exchange=exchange)
+        o.set_parameters(m.parameters())
+        if early:
+            assert o.enable_early_exchange(m), "two-phase exchange did not come up"
+        return m, lf, o
+
+    out = {}
+    for name, (exchange, early) in {"two_phase": ("peer", True), "one_phase": ("peer", False), "nccl": ("nccl", False)}.items():
+        m, lf, o = fresh(exchange, early)
+        if exchange == "peer" and o.peer is None:
+            out[name] = None                              # peer mapping unavailable on this box: reported below
+            continue
+        fwd_bwd(m, lf, rank)
+        o.step()
+        torch.cuda.synchronize()
+        out[name] = o.flat.clone()
+        del m, lf, o
+    res = {"ok": True, "world": world}
+    # 1. replicas bit-identical (for the exchange that is timed, else the first that exists)
+    key = next(k for k in ("two_phase", "one_phase", "nccl") if out.get(k) is not None)
+    iv = out[key].view(torch.int32).to(torch.int64)
+    w = torch.arange(iv.numel(), device=dev, dtype=torch.int64) % 1021 + 1
+    chk = torch.stack([iv.sum(), (iv * w).sum()])
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    res["replicas_bit_identical"] = bool(all(torch.equal(c, allc[0]) for c in allc))
+    res["checked_exchange"] = key
+
+    def frac_off(a, b):
+        bad = ~torch.isclose(a, b, rtol=1e-5, atol=2e-6)  # Adam's first step is lr*g/(|g|+eps): near-zero gradients may flip
+        return float(bad.float().mean()), float((a - b).abs().max())
+    # 2. exchanges agree
+    ex = {}
+    for k in ("one_phase", "nccl"):
+        if out.get(k) is not None and k != key:
+            ex[k + "_vs_" + key] = dict(zip(("frac_off", "max_abs"), frac_off(out[k], out[key])))
+    res["exchanges"] = ex
+    # 3. rank 0: accumulation over the N batches, alone (no collective inside)
+    acc = None
+    if rank == 0:
+        torch.manual_seed(3435)
+        m = vm.make_vi_model_mmt(opt, fields, gpu=True)
+        m.train()
+        lf = vm.NMTVIModel1LossCompute(m.generator, fields["tgt"].vocab)
+        o = vm.Optim("adam", 0.002, 5, exchange="nccl")
+        o.sync_gradients = False
+        o.set_parameters(m.parameters())
+        for r in range(world):
+            fwd_bwd(m, lf, r, zero=(r == 0))
+        o.step()
+        torch.cuda.synchronize()
+        acc = dict(zip(("frac_off", "max_abs"), frac_off(out[key], o.flat)))
+        del m, lf, o
+    res["accumulation_on_rank0"] = acc
+    flags = [res["replicas_bit_identical"]] + [v["frac_off"] < 5e-4 for v in ex.values()]
+    if acc is not None:
+        flags.append(acc["frac_off"] < 5e-4)
+    t = torch.tensor([1 if all(flags) else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    res["ok"] = bool(int(t[0]))
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_generator(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
+    """The largest single GEMM of the step (the fused generator + log-sum-exp forward) in isolation, L2 flushed between
+    iterations, against the measured tensor peak; DESIGN.md ("Measurement") states the algorithmic FLOPs."""
     import torch
     from variational_mmt_b200.ops import fptr, ptr, stream
     H, V, B = mk["hidden"], mk["v"], bk["batch_size"]
@@ -546,7 +803,7 @@ def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
 
     def run():
         _lib.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), 1, M, H, V, fptr(lse),
-                  fptr(stats), fptr(ws), wsb, 0, stream())
+                  fptr(stats), fptr(ws), wsb, vm.ops.flags(), stream())
     for _ in range(3):
         run()
     times = []
@@ -561,7 +818,7 @@ def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
     ms = sorted(times)[len(times) // 2]
     flops = 2.0 * M * H * V
     achieved = flops / (ms * 1e-3) / 1e12
-    peak = peaks["bf16_tflops"] / 2.0        # TF32 runs at half the bf16 tensor rate
+    peak = peaks["bf16_tflops"] / (1.0 if args.dtype == "bf16" else 2.0)       # TF32 runs at half the bf16 tensor rate
     name = "vmmt_generator_nll_fwd (M=%d,H=%d,V=%d)" % (M, H, V)
     traffic = None                           # DRAM bytes per launch from the committed `ncu --set full` capture, if any
     tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
@@ -571,7 +828,8 @@ def roofline(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
     return {"kernel": name, "bound": "tensor",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "algorithmic_bytes": (M * H + V * H + V) * 4.0, "ms": ms,
-            "peak_source": "%s bf16 burst %.0f TF/s / 2 (tf32 operands)" % (how, peaks["bf16_tflops"])}
+            "peak_source": "%s bf16 burst %.0f TF/s%s" % (how, peaks["bf16_tflops"],
+                                                         "" if args.dtype == "bf16" else " / 2 (tf32 operands)")}
 
 
 def main():
@@ -582,7 +840,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS) + ["decode"])
     ap.add_argument("--decode-batch", type=int, default=250, help="sentences decoded together (workload decode)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="f32: TF32 tensor-core operands on fp32 storage (headline); bf16: bf16 operands, fp32 accumulate")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port and the torch-on-GPU yardstick")
+    ap.add_argument("--no-decode", action="store_true", help="skip the short beam-decode run of the default line")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the un-timed data-parallel parity step (N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the baseline sample")
     args = ap.parse_args()

@@ -98,15 +98,23 @@ def _cfg_of(mk):
                              conditional=mk["conditional"])
 
 
-def time_train_steps(mk, bk, steps=3, warmup=1, threads=None, budget_s=25.0, dropout=0.5):
-    """Times full CPU training steps (fwd + loss + bwd + clip + Adam) on synthetic batches of the
-    workload; stops early once `budget_s` seconds of timed work have been spent (>= 1 step)."""
+def time_train_steps(mk, bk, steps=3, warmup=1, threads=None, budget_s=25.0, dropout=0.5, device="cpu"):
+    """Times full training steps (fwd + loss + bwd + clip + Adam) of the port on synthetic batches of the
+    workload; stops early once `budget_s` seconds of timed work have been spent (>= 1 step).
+    ``device="cuda"``: the same torch library calls on the GPU (cuDNN nn.LSTM + cuBLAS: the library path the reference
+    used on its GPUs, README.md:49) -- bench.py's informational ``gpu_torch_baseline`` yardstick."""
     if threads:
         torch.set_num_threads(int(threads))
     cfg = _cfg_of(mk)
     params = synth.make_params(cfg, 3435, 0.1)
     model = CpuStep(cfg, params, dropout=dropout)
     model.train()
+    on_gpu = str(device).startswith("cuda")
+    if on_gpu:
+        model = model.to(device)
+        for rnn in (model.enc, model.dec, getattr(model, "tgt", None)):
+            if rnn is not None:
+                rnn.flatten_parameters()
     opt = torch.optim.Adam(model.parameters(), lr=0.002, betas=(0.9, 0.999), eps=1e-9)
     shard = 32 if mk["hidden"] < 1024 else 128
     batches = [R.to_torch_batch(synth.make_batch(cfg, batch_size=bk["batch_size"], seed=i,
@@ -114,6 +122,12 @@ def time_train_steps(mk, bk, steps=3, warmup=1, threads=None, budget_s=25.0, dro
                                                  src_max=80 if mk["hidden"] >= 1024 else 50,
                                                  tgt_max=80 if mk["hidden"] >= 1024 else 50))
                for i in range(2)]
+    if on_gpu:
+        batches = [{k: v.to(device) for k, v in b.items()} for b in batches]
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
 
     def one(b):
         opt.zero_grad(set_to_none=True)
@@ -130,13 +144,22 @@ def time_train_steps(mk, bk, steps=3, warmup=1, threads=None, budget_s=25.0, dro
 
     for i in range(warmup):
         one(batches[i % 2])
+    sync()
     done, tok, t0 = 0, 0, time.perf_counter()
     for i in range(max(steps, 1)):
         tok += one(batches[i % 2])
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
+    sync()
     dt = time.perf_counter() - t0
+    if on_gpu:
+        return {"tokens_per_s": tok / dt, "ms_per_step": dt / done * 1e3, "steps": done, "warmup": warmup,
+                "tokens_per_step": tok / done,
+                "sample": "%d full training steps of the oracle port on %s: torch %s eager, cuDNN nn.LSTM (allow_tf32=%s) + "
+                          "cuBLAS matmul (allow_tf32=%s), B=%d, host-timed with synchronize" % (
+                              done, torch.cuda.get_device_name(), torch.__version__, torch.backends.cudnn.allow_tf32,
+                              torch.backends.cuda.matmul.allow_tf32, bk["batch_size"])}
     return {"tokens_per_s": tok / dt, "ms_per_step": dt / done * 1e3, "steps": done, "warmup": warmup,
             "threads": torch.get_num_threads(), "tokens_per_step": tok / done,
             "sample": "%d full training steps (fwd+loss+bwd+clip+Adam) of the same workload, B=%d, "

@@ -199,6 +199,11 @@ def main():
         case_decode(ns, "tiny_cond_greedy", synth.TINY, 4, 1)
     if want("tiny_fixed_beam5"):
         case_decode(ns, "tiny_fixed_beam5", synth.TINY_FIXED, 3, 5)
+    # bidirectional source encoder (-encoder_type brnn, opts.py:54-58; Models.py:107-109,1158-1165)
+    if want("tiny_brnn_eval"):
+        case_eval(ns, "tiny_brnn_eval", synth.TINY_BRNN, ragged5)
+    if want("tiny_brnn_train"):
+        case_train(ns, "tiny_brnn_train", synth.TINY_BRNN, dict(batch_size=6, seed=2, t_force=20))
     if want("cfg1_eval"):
         case_eval(ns, "cfg1_eval", synth.CFG1, dict(batch_size=40, seed=3))
     if want("cfg1_train"):

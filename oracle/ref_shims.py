@@ -131,6 +131,8 @@ def load():
                 "-layers", str(cfg.layers), "-dropout", str(cfg.dropout), "-dropout_imgs", "0.5"]
         if cfg.conditional:
             args.append("--conditional")
+        if getattr(cfg, "brnn", False):
+            args += ["-encoder_type", "brnn"]
         opt = prs.parse_args(args + list(extra))
         opt.brnn = (opt.encoder_type == "brnn")
         return opt

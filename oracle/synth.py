@@ -59,6 +59,7 @@ class ModelConfig:
     layers: int = 2
     conditional: bool = True
     dropout: float = 0.0
+    brnn: bool = False      # -encoder_type brnn (opts.py:54-58): bidirectional source encoder, H/2 per direction
 
     def to_dict(self):
         return asdict(self)
@@ -69,6 +70,7 @@ CFG_FIXED = ModelConfig(z_dim=50, conditional=False)           # run_additional_
 CFG5 = ModelConfig(v_src=32000, v_tgt=32000, emb=1024, hidden=1024, z_dim=1024)
 TINY = ModelConfig(v_src=120, v_tgt=150, emb=32, hidden=64, z_dim=24)
 TINY_FIXED = ModelConfig(v_src=120, v_tgt=150, emb=32, hidden=64, z_dim=24, conditional=False)
+TINY_BRNN = ModelConfig(v_src=120, v_tgt=150, emb=32, hidden=64, z_dim=24, brnn=True)
 
 
 def param_shapes(cfg):
@@ -77,12 +79,14 @@ def param_shapes(cfg):
     E, H, Z, D, L = cfg.emb, cfg.hidden, cfg.z_dim, cfg.img_dim, cfg.layers
     s = OrderedDict()
     s["encoder.embeddings.make_embedding.emb_luts.0.weight"] = (cfg.v_src, E)
+    He = H // 2 if cfg.brnn else H                 # Models.py:107-109: hidden_size // num_directions
     for l in range(L):
         i = E if l == 0 else H
-        s[f"encoder.rnn.weight_ih_l{l}"] = (4 * H, i)
-        s[f"encoder.rnn.weight_hh_l{l}"] = (4 * H, H)
-        s[f"encoder.rnn.bias_ih_l{l}"] = (4 * H,)
-        s[f"encoder.rnn.bias_hh_l{l}"] = (4 * H,)
+        for sfx in (("", "_reverse") if cfg.brnn else ("",)):
+            s[f"encoder.rnn.weight_ih_l{l}{sfx}"] = (4 * He, i)
+            s[f"encoder.rnn.weight_hh_l{l}{sfx}"] = (4 * He, He)
+            s[f"encoder.rnn.bias_ih_l{l}{sfx}"] = (4 * He,)
+            s[f"encoder.rnn.bias_hh_l{l}{sfx}"] = (4 * He,)
     s["decoder.embeddings.make_embedding.emb_luts.0.weight"] = (cfg.v_tgt, E)
     for l in range(L):
         i = E + Z if l == 0 else H

@@ -81,7 +81,7 @@ def lstm_stack(x, p, prefix, layers, h0=None, c0=None, lengths=None, bidirection
 def masked_mean(x, lengths):
     """GlobalInferenceNetwork.encode_seq (onmt/modules/NormalVariationalEncoder.py:65-84)."""
     T = x.shape[0]
-    m = (torch.arange(T).unsqueeze(1) < lengths.unsqueeze(0)).to(x.dtype).unsqueeze(2)
+    m = (torch.arange(T, device=x.device).unsqueeze(1) < lengths.unsqueeze(0)).to(x.dtype).unsqueeze(2)
     return (x * m).sum(0) / m.sum(0)
 
 
@@ -99,7 +99,7 @@ def global_attention(q, ctx, lengths, w_in, w_out):
     qb, cb = q.transpose(0, 1), ctx.transpose(0, 1)
     scores = (qb @ w_in.t()) @ cb.transpose(1, 2)                   # [B,T,S]
     if lengths is not None:
-        mask = torch.arange(S).unsqueeze(0) < lengths.unsqueeze(1)  # [B,S]
+        mask = torch.arange(S, device=q.device).unsqueeze(0) < lengths.unsqueeze(1)  # [B,S]
         scores = scores.masked_fill(~mask.unsqueeze(1), float("-inf"))
     align = scores.softmax(-1)
     c = align @ cb
@@ -146,7 +146,12 @@ def forward(p, cfg, batch, training=False, eps=None, drop=None, z_override=None)
     L = cfg.layers
     # 1 encoder (Models.py:131-149)
     x = p["encoder.embeddings.make_embedding.emb_luts.0.weight"][src]
-    ctx, h_enc, c_enc = lstm_stack(x, p, "encoder.rnn", L, lengths=lengths, drop=drop)
+    brnn = getattr(cfg, "brnn", False)
+    ctx, h_enc, c_enc = lstm_stack(x, p, "encoder.rnn", L, lengths=lengths, bidirectional=brnn, drop=drop)
+    if brnn:
+        # RNNVIDecoderBase._fix_enc_hidden (Models.py:1158-1165): [layers*2, B, H/2] -> [layers, B, H], fwd ; bwd per layer
+        h_enc = torch.cat([h_enc[0::2], h_enc[1::2]], 2)
+        c_enc = torch.cat([c_enc[0::2], c_enc[1::2]], 2)
     out = {"context": ctx, "enc_h": h_enc, "enc_c": c_enc}
     hx = masked_mean(ctx, lengths)
     if cfg.conditional:

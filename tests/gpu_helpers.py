@@ -11,7 +11,8 @@ def build_cuda_model(cfg, params, dropout=0.0):
     import variational_mmt_b200 as vm
     from variational_mmt_b200 import synthetic
     opt = synthetic.make_opt(emb=cfg.emb, hidden=cfg.hidden, z_dim=cfg.z_dim, layers=cfg.layers,
-                             conditional=cfg.conditional, dropout=dropout)
+                             conditional=cfg.conditional, dropout=dropout,
+                             encoder_type="brnn" if getattr(cfg, "brnn", False) else "rnn")
     fields = synthetic.make_fields(cfg.v_src, cfg.v_tgt)
     model = vm.make_vi_model_mmt(opt, fields, gpu=True)
     sd = model.state_dict()
@@ -56,3 +57,13 @@ def named_grads(model):
     for k, p in model.named_parameters():
         out[k] = None if p.grad is None else p.grad.detach().cpu().numpy().copy()
     return out
+
+
+def attn_max_rel(a, ref, src_lengths):
+    """north_star's attention criterion: max over UNMASKED entries of |a - ref| / ref (a, ref: [T, B, S])."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    live = np.arange(a.shape[2])[None, None, :] < np.asarray(src_lengths)[None, :, None]
+    live = np.broadcast_to(live, a.shape)
+    assert not np.any(a[~live]), "attention mass on padding"
+    return float((np.abs(a - ref)[live] / ref[live]).max())

@@ -97,7 +97,13 @@ def check_lstm(tol=2e-5):
     cases = [("enc-masked", 30, 40, 500, 500, True, False, False),
              ("dec-h0-rowbias", 31, 40, 500, 500, False, True, True),
              ("tiny-odd", 7, 5, 33, 50, True, True, False),
-             ("tgtenc-bi", 40, 32, 500, 250, False, False, False)]
+             ("tgtenc-bi", 40, 32, 500, 250, False, False, False),
+             # H > 512: beyond the cluster kernel (16 CTAs x 32 units); the REAL dispatch (no environment override) takes
+             # the step-wise GEMM + cell path in tensor-core mode (csrc/lstm_step.cu), masked, with h0/c0, both directions
+             ("wide-stepwise", 6, 9, 96, 600, True, True, False),
+             ("wide-stepwise-bi", 5, 4, 64, 520, False, False, False),
+             # two row groups per cluster (9..16 batch rows: MMA N = 16, two cells per thread)
+             ("two-row-groups", 12, 16, 64, 96, True, True, True)]
     for name, T, N, In, H, masked, with_h0, with_rb in cases:
         ndir = 2 if name.endswith("-bi") else 1
         x = _r(T, N, In, scale=0.5, seed=11).requires_grad_(True)

@@ -104,3 +104,38 @@ def test_batched_decode_cfg1_shape_equals_sentence_by_sentence(cuda_device):
     r3 = tr.translate_batch(t, None, None)
     for j in range(3):
         assert r3["predictions"][j][0] == full["predictions"][100 + j][0]
+
+
+def test_cfg5_dimension_train_step_matches_oracle(cuda_device):
+    """One whole training step at the HIDDEN SIZES of BASELINE configs[4] (E = H = Z = 1024: the step-wise recurrence
+    path for H > 512, 128-wide row-MLP tiles, K = 4096 posterior) on a reduced batch and vocabulary so that the CPU
+    oracle finishes in seconds; benchmarked arithmetic (TF32 tensor cores), tolerances of test_gpu_parity.py."""
+    import variational_mmt_b200 as vm
+    from gpu_helpers import build_cuda_model, to_device, named_grads, relerr, attn_max_rel
+    from oracle import synth
+    from oracle import vi_model1_ref as R
+    cfg = synth.ModelConfig(v_src=2000, v_tgt=2000, emb=1024, hidden=1024, z_dim=1024)
+    params = synth.make_params(cfg, 3435, 0.05)
+    batch = synth.make_batch(cfg, batch_size=6, seed=9, t_force=14, s_force=12)
+    model, fields = build_cuda_model(cfg, params)
+    model.train()
+    b = to_device(batch)
+    loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+    model.zero_grad()
+    with vm.Normal.inject_noise(b.eps):
+        out, attns, _ = model(b.src, b.tgt_in, b.src_lengths, b.tgt_lengths, b.img_feats)
+    st = loss.sharded_compute_loss(b, out, attns, 0, b.tgt.size(0), 32, b.batch_size)
+    torch.cuda.synchronize()
+    ograds, ostats, ofwd = R.train_step_grads(params, cfg, batch)
+    assert st.n_words == ostats["n_words"]
+    assert st.nmt_loss == pytest.approx(ostats["nmt"], rel=1e-3)
+    assert st.td_kl_before == pytest.approx(ostats["td_kl_before"], rel=1e-3)
+    assert st.image_feats_loss == pytest.approx(ostats["img_feats_loss"], rel=1e-3)
+    assert attn_max_rel(attns["std"].detach().cpu().numpy(), ofwd["attn"].detach().numpy(), batch.src_lengths) <= 1e-3
+    grads = named_grads(model)
+    for k, og in ograds.items():
+        if og is None or not np.any(og.numpy()):
+            continue
+        floor = 1e-4 * float(np.abs(og.numpy()).max())
+        err = np.linalg.norm(grads[k].astype(np.float64) - og.numpy()) / max(np.linalg.norm(og.numpy()), floor)
+        assert err <= 3e-2, f"grad {k}: rel err {err:.3e}"

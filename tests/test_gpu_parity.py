@@ -1,21 +1,24 @@
 """-m gpu: the CUDA path (through the mirrored module API -> ctypes -> libvmmt C ABI) against the
 CPU oracle and against the golden fixtures of the executed reference.
 
-Tolerances (north_star): loss / KL / attention within 1e-3 relative in the fp32 configuration.  The
-"exact fp32" GEMM mode (SIMT) is held to much tighter bounds (1e-4) so that logic errors cannot hide
-inside the tensor-core rounding budget; the default (TF32 tcgen05 GEMMs) gets the 1e-3 budget."""
+Tolerances (north_star): loss / KL / attention within 1e-3 RELATIVE in the fp32 configuration -- for the attention
+weights that is max |a - ref| / ref over every unmasked entry, against the oracle's full tensor.  The "exact fp32" mode
+(SIMT) is held to much tighter bounds (2e-5) so that logic errors cannot hide inside the tensor-core rounding budget;
+the benchmarked default (TF32 tcgen05 GEMMs + fp16-operand recurrence, exact-fp32 batch-row networks) gets the 1e-3
+budget.  Measured maxima at config 1 (tools/parity_probe.py, profiles/parity_r2.txt): 1.2e-4 eval, 6.4e-4 conditional
+training, 2.5e-4 fixed-prior training."""
 import numpy as np
 import pytest
 import torch
 
 from conftest import load_golden, golden_sample
-from gpu_helpers import build_cuda_model, to_device, relerr, maxabs, named_grads
+from gpu_helpers import build_cuda_model, to_device, relerr, maxabs, named_grads, attn_max_rel
 from oracle import synth
 from oracle import vi_model1_ref as R
 
 pytestmark = pytest.mark.gpu
 
-# (gemm mode, rel tol on losses, abs tol on attention, rel-norm tol on gradients)
+# (gemm mode, rel tol on losses, abs tol on the other forward tensors / REL tol on attention, rel-norm tol on gradients)
 # TF32 gradient budget: operand rounding alone is ~1e-3; the rest is ReLU masks of the small MLPs flipping for
 # pre-activations within rounding distance of zero (each flipped unit changes whole rows of a weight gradient)
 MODES = {"fp32_simt": (1, 2e-5, 2e-5, 2e-4), "tf32_tc": (0, 1e-3, 1e-3, 3e-2)}
@@ -47,7 +50,7 @@ def _stats_of(st):
                 n_words=st.n_words, n_correct=st.n_correct)
 
 
-@pytest.mark.parametrize("name", ["tiny_cond_eval", "tiny_fixed_eval", "cfg1_eval"])
+@pytest.mark.parametrize("name", ["tiny_cond_eval", "tiny_fixed_eval", "tiny_brnn_eval", "cfg1_eval"])
 def test_eval_forward_matches_reference(name, mode):
     ltol, atol, _ = mode
     meta, arr, cfg, params, batch = _setup(name)
@@ -65,6 +68,9 @@ def test_eval_forward_matches_reference(name, mode):
                img_loc=attns["p_global_image_features"][0].params()[0])
     for k, v in got.items():
         assert maxabs(golden_sample(v.cpu().numpy()), arr[k]) <= atol + 10 * atol * np.abs(arr[k]).max(), k
+    ofwd, _, _ = R.eval_step(params, cfg, batch)
+    rel = attn_max_rel(attns["std"].cpu().numpy(), ofwd["attn"].numpy(), batch.src_lengths)
+    assert rel <= atol, f"attention max relative error {rel:.3e}"
     ref = meta["stats"]
     s = _stats_of(st)
     for k in STAT_KEYS:
@@ -74,7 +80,8 @@ def test_eval_forward_matches_reference(name, mode):
         assert abs(s["n_correct"] - ref["n_correct"]) <= 1
 
 
-@pytest.mark.parametrize("name", ["tiny_cond_train", "tiny_fixed_train", "cfg1_train", "cfg1_fixed_train"])
+@pytest.mark.parametrize("name", ["tiny_cond_train", "tiny_fixed_train", "tiny_brnn_train", "cfg1_train",
+                                  "cfg1_fixed_train"])
 def test_train_step_matches_reference(name, mode):
     """forward (injected noise) + sharded loss + backward + clip/Adam against the executed reference
     (golden) and, tensor by tensor, against the oracle's full gradients."""
@@ -98,7 +105,9 @@ def test_train_step_matches_reference(name, mode):
     assert maxabs(golden_sample(attns["std"].detach().cpu().numpy()), arr["attn"]) <= atol
     # gradients: golden norms + oracle full tensors
     grads = named_grads(model)
-    ograds, _, _ = R.train_step_grads(params, cfg, batch)
+    ograds, _, ofwd = R.train_step_grads(params, cfg, batch)
+    rel = attn_max_rel(attns["std"].detach().cpu().numpy(), ofwd["attn"].detach().numpy(), batch.src_lengths)
+    assert rel <= atol, f"attention max relative error {rel:.3e}"
     gn = meta["extra"]["grad_norm"]
     total = 0.0
     for k, ref_norm in gn.items():
@@ -176,3 +185,79 @@ def test_graphed_step_draws_fresh_noise_each_replay(cuda_device):
     v2 = step(*args).cpu().numpy().copy()
     assert v1[0] != v2[0] and v1[3] != v2[3]
     assert abs(v1[0] - v2[0]) < 0.2 * abs(v1[0])
+
+
+def test_global_attention_one_step_2d_input_matches_oracle(mode):
+    """GlobalAttention.forward with 2-D input = one decoding step (onmt/modules/GlobalAttention.py:147-151,192-202):
+    returns attn_h [batch, dim] and align [batch, src_len]; checked against the oracle's sequence form with T = 1."""
+    _, atol, _ = mode
+    import variational_mmt_b200 as vm
+    B, S, H = 7, 11, 64
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B, H, generator=g) * 0.5
+    ctx = torch.randn(B, S, H, generator=g) * 0.5
+    lengths = torch.tensor([11, 11, 9, 7, 4, 2, 1])
+    attn = vm.GlobalAttention(H, attn_type="general").cuda()
+    with torch.no_grad():
+        attn.linear_in.weight.copy_(torch.randn(H, H, generator=g) * 0.1)
+        attn.linear_out.weight.copy_(torch.randn(H, 2 * H, generator=g) * 0.1)
+        h1, a1 = attn(q.cuda(), ctx.cuda(), context_lengths=lengths.cuda())
+        assert h1.shape == (B, H) and a1.shape == (B, S)
+        # the 3-D form with tgt_len = 1 must give the same numbers
+        h3, a3 = attn(q.cuda().unsqueeze(1), ctx.cuda(), context_lengths=lengths.cuda())
+        assert h3.shape == (1, B, H) and a3.shape == (1, B, S)
+        assert torch.equal(h3[0], h1) and torch.equal(a3[0], a1)
+    oh, oa = R.global_attention(q.unsqueeze(0), ctx.transpose(0, 1), lengths, attn.linear_in.weight.cpu(),
+                                attn.linear_out.weight.cpu())
+    assert attn_max_rel(a1.cpu().numpy()[None], oa.detach().numpy(), lengths.numpy()) <= atol
+    assert maxabs(h1.cpu().numpy(), oh[0].detach().numpy()) <= 10 * atol
+
+
+@pytest.mark.parametrize("name", ["tiny_cond_train", "tiny_brnn_train"])
+def test_train_step_with_dropout_masks_matches_oracle(name, mode):
+    """Dropout 0.5 at all four sites (LSTM inter-layer x3 stacks, decoder output: hazard H7) with the SAME masks on both
+    sides: the in-kernel Philox masks of the CUDA step are regenerated (ops.dropout_mask: same seed / offset / step base)
+    and handed to the oracle's drop(x, site) callback.  Losses, attention and every gradient must then agree as in the
+    dropout-free fixtures."""
+    ltol, atol, gtol = mode
+    meta, arr, cfg, params, batch = _setup(name)
+    import variational_mmt_b200 as vm
+    from variational_mmt_b200 import ops
+    model, fields = build_cuda_model(cfg, params, dropout=0.5)
+    model.train()
+    b = to_device(batch)
+    loss = vm.NMTVIModel1LossCompute(model.generator, fields["tgt"].vocab)
+    ops.manual_seed(1234)
+    ops.begin_step()
+    log = []
+    ops.set_dropout_log(log)
+    try:
+        model.zero_grad()
+        with vm.Normal.inject_noise(b.eps):
+            out, attns, _ = model(b.src, b.tgt_in, b.src_lengths, b.tgt_lengths, b.img_feats)
+        st = loss.sharded_compute_loss(b, out, attns, 0, b.tgt.size(0), 32, b.batch_size)
+    finally:
+        ops.set_dropout_log(None)
+    # forward call order (Models.NMTVIModel.forward): target encoder (conditional), source encoder, decoder layer, output
+    sites = (["encoder_tgt.rnn.l1"] if cfg.conditional else []) + ["encoder.rnn.l1", "decoder.rnn.l1", "decoder.out"]
+    assert len(log) == len(sites), log
+    masks = {s: ops.dropout_mask(shape, p, seed, offset).cpu() for s, (shape, p, seed, offset) in zip(sites, log)}
+    for s, m in masks.items():
+        keep = float((m > 0).float().mean())
+        assert 0.3 < keep < 0.7 and float(m.max()) == 2.0, (s, keep)
+
+    def drop(x, site):
+        m = masks[site]
+        assert m.shape == x.shape, (site, m.shape, x.shape)
+        return x * m.to(x.dtype)
+    ograds, ostats, ofwd = R.train_step_grads(params, cfg, batch, drop=drop)
+    assert st.n_words == ostats["n_words"]
+    assert st.nmt_loss == pytest.approx(ostats["nmt"], rel=ltol, abs=ltol)
+    assert st.td_kl_before == pytest.approx(ostats["td_kl_before"], rel=ltol, abs=ltol)
+    assert st.image_feats_loss == pytest.approx(ostats["img_feats_loss"], rel=ltol, abs=ltol)
+    assert attn_max_rel(attns["std"].detach().cpu().numpy(), ofwd["attn"].detach().numpy(), batch.src_lengths) <= atol
+    grads = named_grads(model)
+    for k, og in ograds.items():
+        if og is None or not np.any(og.numpy()):
+            continue
+        assert relerr(grads[k], og.numpy()) <= gtol, f"grad {k}: rel err {relerr(grads[k], og.numpy()):.3e}"

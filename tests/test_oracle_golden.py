@@ -34,7 +34,7 @@ def _check_stats(stats, ref, rtol=2e-5):
     assert stats["n_correct"] == ref["n_correct"]
 
 
-@pytest.mark.parametrize("name", ["tiny_cond_eval", "tiny_fixed_eval", "cfg1_eval"])
+@pytest.mark.parametrize("name", ["tiny_cond_eval", "tiny_fixed_eval", "tiny_brnn_eval", "cfg1_eval"])
 def test_eval_forward_and_loss(name):
     meta, arr, cfg, params = _setup(name)
     batch = synth.make_batch(cfg, **meta["batch"])
@@ -44,7 +44,7 @@ def test_eval_forward_and_loss(name):
     _check_stats(stats, meta["stats"])
 
 
-@pytest.mark.parametrize("name", ["tiny_cond_train", "tiny_fixed_train", "cfg1_train",
+@pytest.mark.parametrize("name", ["tiny_cond_train", "tiny_fixed_train", "tiny_brnn_train", "cfg1_train",
                                   "cfg1_fixed_train"])
 def test_train_step_grads_and_update(name):
     meta, arr, cfg, params = _setup(name)

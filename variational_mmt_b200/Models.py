@@ -141,9 +141,10 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         self.encoder_tgt = kwargs["encoder_tgt"] if self.conditional else None
         if self.encoder_tgt is not None:
             self.encoder_tgt.no_pack_padded_seq = True
-            # concurrent source / target encoders (training): 3 + 4 of the ~7 GPC-sized cluster slots of a B200
+            # concurrent source / target encoders (training): 5 clusters of 16 CTAs (8 batch rows each: the one-row-group
+            # kernel) beside 8 clusters of 8 CTAs = 144 of the 148 SMs
             self.encoder_tgt.rnn.fires_early_exchange = True
-            self.encoder.rnn.cluster_budget = int(os.environ.get("VMMT_ENC_BUDGET", "3")) or None
+            self.encoder.rnn.cluster_budget = int(os.environ.get("VMMT_ENC_BUDGET", "5")) or None
             self.encoder_tgt.rnn.cluster_budget = int(os.environ.get("VMMT_TGT_BUDGET", "8")) or None
         self.inf_net_global = kwargs["inf_net_global"]
         self.gen_net_global = kwargs["gen_net_global"]

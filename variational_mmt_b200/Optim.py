@@ -28,6 +28,33 @@ class _ParamList(torch.nn.Module):
         self.plist = torch.nn.ParameterList(params)
 
 
+class _AdamStateView(object):
+    """What the reference's callers reach through ``optim.optimizer`` (a torch.optim.Adam there, onmt/Optim.py:69-70):
+    ``state_dict()`` / ``load_state_dict()`` (train_mm_vi_model1.py:433-437) and ``param_groups[0]['lr']``.  The state is
+    the flat Adam moments of the fused kernels: {"step", "exp_avg", "exp_avg_sq"} as host tensors over the flat parameter
+    buffer.  With the NVLink peer exchange every rank holds only its slice of the moments: state_dict() is then COLLECTIVE
+    (one all-reduce assembles the full vectors on every rank) -- call it on all ranks, write the file on one."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    @property
+    def param_groups(self):
+        o = self._o
+        return [{"lr": o.lr, "betas": tuple(o.betas), "eps": 1e-9}]
+
+    def state_dict(self):
+        return self._o._adam_state_dict()
+
+    def load_state_dict(self, sd):
+        self._o._load_adam_state(sd)
+
+
+# device / process bound attributes: dropped when an Optim is pickled into a checkpoint (TrainerMultimodal.py:576-587)
+_UNPICKLED = ("params", "flat", "gflat", "exp_avg", "exp_avg_sq", "_gsum", "_pws", "_sq", "_ws", "peer", "_early",
+              "_owner", "optimizer")
+
+
 class Optim(object):
     def __init__(self, method, lr, max_grad_norm, lr_decay=1, start_decay_at=None, beta1=0.9, beta2=0.999,
                  adagrad_accum=0.0, decay_method=None, warmup_steps=4000, model_size=None, exchange="auto"):
@@ -39,14 +66,83 @@ class Optim(object):
         self.lr_decay, self.start_decay_at, self.start_decay = lr_decay, start_decay_at, False
         self._step = 0
         self.betas = [beta1, beta2]
+        self.adagrad_accum = adagrad_accum   # kept for checkpoint compatibility (adagrad is not on the published path)
         self.decay_method, self.warmup_steps, self.model_size = decay_method, warmup_steps, model_size
         self.sync_gradients = True           # all-reduce across ranks when torch.distributed is up
         self.exchange = exchange
         self.peer = None                     # distributed.PeerExchange when the NVLink peer path is active
         self._early = None                   # early (overlapped) exchange of the tail of the flat buffer, see enable_early_exchange
         self._early_done = False
+        self._adam_t = 0                     # Adam's bias-correction step (torch.optim.Adam's state['step']; restarts with
+        #                                      every set_parameters, exactly as the reference's fresh optim.Adam does)
+        self._pending_state = None           # Adam state carried by an unpickled / not yet bound Optim
+        self.optimizer = _AdamStateView(self)
 
-    def set_parameters(self, params):
+    # ---- checkpointing (TrainerMultimodal.py:576-587 pickles the whole Optim; train_mm_vi_model1.py:433-452 resumes) ----
+    def __getstate__(self):
+        d = {k: v for k, v in self.__dict__.items() if k not in _UNPICKLED}
+        d["_pending_state"] = self._adam_state_dict() if getattr(self, "flat", None) is not None else self._pending_state
+        d["_early_done"] = False
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.peer, self._early = None, None
+        self.optimizer = _AdamStateView(self)
+
+    def _moment_slices(self):
+        """[(moment tensor m, moment tensor v, first float, count)] of what this rank holds."""
+        n = self.flat.numel()
+        if self.peer is not None and self._early is not None:
+            e, pe, b0 = self._early, self.peer, self._early["begin"]
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            out = []
+            L.lib.vmmt_peer_slice(n - b0, pe.world, pe.rank, ctypes.byref(lo), ctypes.byref(hi))
+            out.append((e["m_a"], e["v_a"], b0 + lo.value, hi.value - lo.value))
+            L.lib.vmmt_peer_slice(b0, pe.world, pe.rank, ctypes.byref(lo), ctypes.byref(hi))
+            out.append((e["m_b"], e["v_b"], lo.value, hi.value - lo.value))
+            return out
+        if self.peer is not None:
+            lo, hi, _cap = self.peer.slice_bounds()
+            return [(self.exp_avg, self.exp_avg_sq, lo, hi - lo)]
+        return [(self.exp_avg, self.exp_avg_sq, 0, n)]
+
+    def _adam_state_dict(self):
+        if getattr(self, "flat", None) is None:
+            return self._pending_state
+        n = self.flat.numel()
+        m = torch.zeros(n, device=self.flat.device, dtype=torch.float32)
+        v = torch.zeros_like(m)
+        for sm, sv, lo, cnt in self._moment_slices():
+            m[lo:lo + cnt].copy_(sm[:cnt])
+            v[lo:lo + cnt].copy_(sv[:cnt])
+        if self.peer is not None and self.peer.world > 1:
+            torch.distributed.all_reduce(m)              # disjoint slices: the sum assembles the full vectors
+            torch.distributed.all_reduce(v)
+        return {"step": int(self._adam_t), "numel": n, "exp_avg": m.cpu(), "exp_avg_sq": v.cpu(),
+                "param_groups": self.optimizer.param_groups}
+
+    def _load_adam_state(self, sd):
+        if sd is None:
+            return
+        if getattr(self, "flat", None) is None:
+            self._pending_state = sd
+            return
+        if int(sd["numel"]) != self.flat.numel():
+            raise ValueError("Optim: optimizer state of %d elements does not fit %d parameters" % (sd["numel"], self.flat.numel()))
+        dev = self.flat.device
+        m, v = sd["exp_avg"].to(dev), sd["exp_avg_sq"].to(dev)
+        for sm, sv, lo, cnt in self._moment_slices():
+            sm[:cnt].copy_(m[lo:lo + cnt])
+            sv[:cnt].copy_(v[lo:lo + cnt])
+        self._adam_t = int(sd["step"])
+
+    def set_parameters(self, params, keep_state=False):
+        """Bind to the model's parameters (onmt/Optim.py:55-70).  As in the reference, where this builds a NEW
+        torch.optim.Adam, the Adam moments and bias-correction step start from zero -- also after ``-train_from``
+        (train_mm_vi_model1.py:433-452 loads the state into the old optimiser object and then rebuilds it here), while
+        ``_step`` / ``lr`` / decay bookkeeping survive in the pickled Optim.  ``keep_state=True`` restores the moments an
+        unpickled Optim carries (or that ``optimizer.load_state_dict`` stored) instead: a true resume."""
         self.params = [p for p in params if p.requires_grad]
         ptrs = {p.data.untyped_storage().data_ptr() for p in self.params}
         grads_ok = all(p.grad is not None for p in self.params) and \
@@ -91,6 +187,11 @@ class Optim(object):
             self.exp_avg_sq = torch.zeros_like(self.flat)
         self._sq = torch.zeros(1, device=p0.device, dtype=torch.float32)
         self._ws = torch.empty(L.lib.vmmt_sqnorm_workspace_bytes() // 4, device=p0.device, dtype=torch.float32)
+        self._adam_t = 0
+        self._early, self._early_done = None, False
+        if keep_state and self._pending_state is not None:
+            self._load_adam_state(self._pending_state)
+        self._pending_state = None
 
     def enable_early_exchange(self, model):
         """Split the peer exchange in two: the gradients of the latent / image networks and the generator (the tail of
@@ -101,8 +202,9 @@ class Optim(object):
         step(): with gradient accumulation over several backward passes the tail is not final when the first pass
         reaches the encoders -- leave it disabled there.  Returns True when active (False: single rank, NCCL exchange,
         VMMT_DP_OVERLAP=0, or a model whose loss-side modules are not the tail of the flat buffer)."""
-        if self.peer is None or self._step != 0 or os.environ.get("VMMT_DP_OVERLAP", "1") == "0":
+        if self.peer is None or os.environ.get("VMMT_DP_OVERLAP", "1") == "0":
             return False
+        carried = self._adam_state_dict() if self._adam_t != 0 else None      # re-partitioning keeps restored moments
         begin = distributed.early_final_begin(model)
         n = self.flat.numel()
         if begin is None or begin % 4 or begin <= 0 or begin >= n:
@@ -118,6 +220,8 @@ class Optim(object):
                        "stream": torch.cuda.Stream(device=dev, priority=-1)}
         self.exp_avg = self.exp_avg_sq = self._gsum = None       # replaced by the per-range slices above
         model.early_exchange_hook = self.early_reduce_scatter
+        if carried is not None:
+            self._load_adam_state(carried)
         torch.cuda.synchronize(dev)
         return True
 
@@ -167,13 +271,16 @@ class Optim(object):
         """Global L2 norm of the (all-reduced) gradient as a device scalar tensor.  With the peer exchange the summed
         gradient never exists in one place: the value is the norm the last step() clipped with (before any step: the
         norm of this rank's own gradients)."""
-        if self.peer is not None and self._step > 0:
+        if self.peer is not None and self._adam_t > 0:
             return self._sq.sqrt()
         L.call("vmmt_sqnorm", fptr(self.gflat), self.gflat.numel(), fptr(self._sq), 0, fptr(self._ws), stream())
         return self._sq.sqrt()
 
     def step(self):
+        """clip + update (+ gradient exchange).  Stays OUTSIDE captured CUDA graphs: the learning rate and Adam's bias
+        corrections are host scalars of each call."""
         self._step += 1
+        self._adam_t += 1
         ops.join_side()
         if self.decay_method == "noam":
             self._set_rate(self.original_lr * (self.model_size ** (-0.5) *
@@ -187,7 +294,7 @@ class Optim(object):
             torch.cuda.current_stream(self.flat.device).wait_stream(e["stream"])
             self._early_done = False
             b0, sm = e["begin"], stream()
-            hyp = (max_norm, float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._step)
+            hyp = (max_norm, float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._adam_t)
             L.call("vmmt_peer_reduce_scatter", pe.segments, pe.grad_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]), 0,
                    fptr(self._pws), sm)
             L.call("vmmt_peer_adam_allgather", pe.segments, pe.param_off, pe.rank, pe.world, b0, n - b0, fptr(e["gsum_a"]),
@@ -199,7 +306,7 @@ class Optim(object):
             pe = self.peer
             L.call("vmmt_peer_adam_step", pe.segments, pe.param_off, pe.grad_off, pe.rank, pe.world, n,
                    fptr(self._gsum), fptr(self.exp_avg), fptr(self.exp_avg_sq), fptr(self._sq), max_norm,
-                   float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._step, fptr(self._pws),
+                   float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._adam_t, fptr(self._pws),
                    stream())
             return
         if self.sync_gradients:
@@ -209,11 +316,13 @@ class Optim(object):
         if self.method == "adam":
             L.call("vmmt_adam_clip_step", fptr(self.flat), fptr(self.gflat), fptr(self.exp_avg),
                    fptr(self.exp_avg_sq), n, fptr(self._sq), max_norm, 1.0, float(self.lr),
-                   float(self.betas[0]), float(self.betas[1]), 1e-9, self._step, stream())
+                   float(self.betas[0]), float(self.betas[1]), 1e-9, self._adam_t, stream())
         else:
-            if max_norm > 0:
-                raise NotImplementedError("sgd with clipping is not on the published path")
-            L.call("vmmt_axpy", fptr(self.flat), fptr(self.gflat), -float(self.lr), n, stream())
+            coef = 1.0
+            if max_norm > 0:                                  # clip_grad_norm semantics (onmt/Optim.py:94-95); sgd is not the
+                norm = float(self._sq) ** 0.5                 # published method: the host read of the norm is accepted here
+                coef = min(1.0, max_norm / (norm + 1e-6))
+            L.call("vmmt_axpy", fptr(self.flat), fptr(self.gflat), -float(self.lr) * coef, n, stream())
 
     def update_learning_rate(self, ppl, epoch):
         if self.start_decay_at is not None and epoch >= self.start_decay_at:

@@ -61,10 +61,10 @@ extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float*
     fprintf(stderr, "[vmmt_gemm] M=%d N=%d K=%d lda=%lld(%s) ldb=%lld(%s) ldc=%lld bias=%d act=%d acc=%d -> %s\n", M, N, K,
             (long long)lda, a_kmajor ? "k" : "mn", (long long)ldb, b_kmajor ? "k" : "mn", (long long)ldc, bias != nullptr,
             act, accumulate,
-            (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K))
+            (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, flags))
                 ? "tcgen05" : "simt");
   if (!(flags & VMMT_F_EXACT) &&
-      vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K)) {
+      vmmt_gemm_tc_eligible(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, flags)) {
     return vmmt_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, flags, s);
   }
   return vmmt_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, bias, act, accumulate, s);
@@ -78,8 +78,8 @@ extern "C" int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, in
   VMMT_REQUIRE(M >= 0 && N >= 0 && K1 >= 1 && K2 >= 1, "gemm_dual: bad dims");
   VMMT_REQUIRE(A1 && B1 && A2 && B2 && C, "gemm_dual: null operand");
   cudaStream_t s = (cudaStream_t)stream;
-  if (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1) &&
-      vmmt_gemm_tc_eligible(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2)) {
+  if (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, flags) &&
+      vmmt_gemm_tc_eligible(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2, flags)) {
     // each pair has its own tensor maps, so a ragged K tail of either is zero-filled by the TMA independently
     VmmtGemmSecond second{A2, lda2, B2, ldb2, K2};
     return vmmt_gemm_tc_dual(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, bias, act, 0, nullptr, &second, flags, s);

@@ -670,7 +670,7 @@ int launch_major(bool a_mn, bool b_mn, const Maps& m, const GemmArgs& g, dim3 gr
 }  // namespace
 
 bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
-                           const float* C, int64_t ldc, int M, int N, int K) {
+                           const float* C, int64_t ldc, int M, int N, int K, int flags) {
   (void)C; (void)ldc; (void)a_kmajor; (void)b_kmajor;
   if (M < 1 || N < 1 || K < 1) return false;
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return false;      // TMA: 16-byte aligned base ...
@@ -680,7 +680,10 @@ bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const floa
   // with split-K over all SMs and the TMA reduce-add epilogue.
   // (K >= 16: the K = batch-size weight-gradient products dW += dY^T X of the batch-row MLPs are 1-2 k-blocks deep but
   //  up to 2048 x 2048 wide -- 40+ us each on the SIMT kernel, a few us here)
-  if (N < 64 || K < 16 || (int64_t)M * N * K < (int64_t)64 * 64 * 64) return false;
+  if (N < 64 || K < 16) return false;
+  // batch-invariant calls (VMMT_F_NO_SPLITK): which kernel runs must not depend on the row count either, or a sentence
+  // decoded alone (M = beam rows) would take the exact SIMT kernel and the same sentence in a batch the TF32 one
+  if (!(flags & VMMT_F_NO_SPLITK) && (int64_t)M * N * K < (int64_t)64 * 64 * 64) return false;
   return true;
 }
 

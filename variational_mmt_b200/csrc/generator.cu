@@ -157,7 +157,7 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
   // tensor-core mode: log-sum-exp / target logit / argmax are folded into the GEMM epilogue; the logits of a tile
   // live in tensor memory and registers only.  Partials: [ceil(V/128)][M] float4 at the head of the workspace.
   if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_GEN_UNFUSED") &&
-      vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) {
+      vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H, flags)) {
     const int ntile = ceil_div(V, 128);
     float* part = logits;                                  // ntile * M * 4 floats  <<  M * V
     float* tgt_logit = part + (size_t)ntile * M * 4;
@@ -194,7 +194,7 @@ extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const floa
   int rc = VMMT_EINVAL;
   // tensor-core mode: the recomputed logits are turned into dlogits in the GEMM epilogue (one pass over M x V)
   if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_GEN_UNFUSED") && (V & 3) == 0 &&
-      vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, dl, V, M, V, H)) {
+      vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, dl, V, M, V, H, flags)) {
     VmmtGenEpi epi{2, nullptr, nullptr, target, lse, gscale, scale, (long long)pad_idx};
     rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, s);
   }
@@ -245,7 +245,7 @@ extern "C" size_t vmmt_generator_topk_workspace_bytes(int M, int V, int K) {
 }
 
 extern "C" int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, int V, int flags) {
-  return (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H)) ? 1 : 0;
+  return (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, nullptr, V, M, V, H, flags)) ? 1 : 0;
 }
 
 extern "C" int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, int H, int V, int K,

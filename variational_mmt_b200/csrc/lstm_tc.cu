@@ -213,12 +213,15 @@ struct TcFwdParams {
   VmmtLstmDir d[2];
   const int64_t* lengths;
   int T, N, H, C, G, Ng, Kp;
+  int floor;            // measurement only (env VMMT_LSTM_FLOOR): one k-block of MMAs and no transcendentals per step --
+                        // what is left is the synchronisation floor (hand-off + mbarriers + tcgen05.ld + gate exchange)
   long long* trace;
 };
 struct TcBwdParams {
   VmmtLstmDirBwd d[2];
   const int64_t* lengths;
   int T, N, H, C, G, Ng, Kp;
+  int floor;
   long long* trace;
 };
 
@@ -457,7 +460,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
         if (tr) P.trace[14] = clock64();
         // k-step j of block kb accumulates into chain j: four independent accumulator chains, 2 k-chunks per k-step
         const uint32_t bd = bd_lo0 + (uint32_t)buf * (tile_bytes >> 4);
-        if (nkb == 8) issue_fwd_mmas<NRG, 8>(bd, bd_hi, idesc);          // H in (448, 512]: every offset an immediate
+        if (P.floor) issue_fwd_mmas<NRG, 1>(bd, bd_hi, idesc);
+        else if (nkb == 8) issue_fwd_mmas<NRG, 8>(bd, bd_hi, idesc);     // H in (448, 512]: every offset an immediate
         else if (nkb == 4) issue_fwd_mmas<NRG, 4>(bd, bd_hi, idesc);     // H in (192, 256]
         else {
           uint32_t a = 0, b = bd;
@@ -514,7 +518,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
           const float Gg = __fadd_rn(gsm[(2 * NPc + n) * 32 + lane], gx[r][2]);
           const float Go = __fadd_rn(gsm[(3 * NPc + n) * 32 + lane], gx[r][3]);
           if (tr && tid == 0 && r == 0) P.trace[16] = clock_after(Gi + Gf + Gg + Go);
-          av[r][0] = fsigmoid(Gi); av[r][1] = fsigmoid(Gf); av[r][2] = ftanh(Gg); av[r][3] = fsigmoid(Go);
+          if (P.floor) { av[r][0] = Gi; av[r][1] = Gf; av[r][2] = Gg; av[r][3] = Go; }
+          else { av[r][0] = fsigmoid(Gi); av[r][1] = fsigmoid(Gf); av[r][2] = ftanh(Gg); av[r][3] = fsigmoid(Go); }
         }
       }
 #pragma unroll
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
         if (r < nr) {
           const int n = warp + 8 * r;
           const float cn = __fmaf_rn(av[r][1], c[r], __fmul_rn(av[r][0], av[r][2]));
-          const float hn = __fmul_rn(av[r][3], ftanh(cn));
+          const float hn = P.floor ? cn : __fmul_rn(av[r][3], ftanh(cn));
           const bool m = t < len[r];
           c[r] = m ? cn : c[r];
           h[r] = m ? hn : h[r];
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       if (leader) {
         mbar_arrive_expect_tx(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)C * part_bytes);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int mt = 0; mt < n_mt; ++mt) {
+        for (int mt = 0; mt < (P.floor ? 1 : n_mt); ++mt) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)                    // K = 128 gate rows = 8 steps of 16
             umma_f16_ts2(TMEM_D + mt * 32, (uint32_t)(mt * 64 + ks * 8),
@@ -1000,6 +1005,7 @@ int vmmt_lstm_tc_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, 
   if (ndir == 1) P.d[1] = dirs[0];
   P.lengths = lengths;
   P.T = T; P.N = N; P.H = H; P.C = p.C; P.G = p.G; P.Ng = p.Ng; P.Kp = p.Kp;
+  P.floor = getenv("VMMT_LSTM_FLOOR") ? 1 : 0;
   P.trace = nullptr;
   return p.nrg == 1 ? launch_fwd<1>(P, p, ndir, maxc, s) : launch_fwd<2>(P, p, ndir, maxc, s);
 }
@@ -1017,6 +1023,7 @@ int vmmt_lstm_tc_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* length
   if (ndir == 1) P.d[1] = dirs[0];
   P.lengths = lengths;
   P.T = T; P.N = N; P.H = H; P.C = p.C; P.G = p.G; P.Ng = p.Ng; P.Kp = p.Kp;
+  P.floor = getenv("VMMT_LSTM_FLOOR") ? 1 : 0;
   P.trace = nullptr;
   return p.nrg == 1 ? launch_bwd<1>(P, p, ndir, maxc, s) : launch_bwd<2>(P, p, ndir, maxc, s);
 }

@@ -44,4 +44,4 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
                       int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate,
                       const VmmtGenEpi* epi, const VmmtGemmSecond* second, int flags, cudaStream_t s);
 bool vmmt_gemm_tc_eligible(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb,
-                           int b_kmajor, const float* C, int64_t ldc, int M, int N, int K);
+                           int b_kmajor, const float* C, int64_t ldc, int M, int N, int K, int flags = 0);

@@ -87,9 +87,21 @@ class GraphedTrainStep(object):
         # must not happen inside the capture
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self._run(*static, normalization)
+        # The warm-up passes must NOT fire the data-parallel early exchange: it is a cross-rank barrier + peer reads of every
+        # rank's gradient segment, and the ranks meet new shape buckets at different steps (io.OrderedIterator deals each
+        # rank its own batches) -- a capturing rank would run two barrier generations ahead of a replaying one.  The
+        # exchange is part of the CAPTURED step only (recorded here, executed by every rank once per replay).
+        hook = getattr(self.model, "early_exchange_hook", None)
+        early_done = getattr(self.optim, "_early_done", False) if self.optim is not None else False
+        self.model.early_exchange_hook = None
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._run(*static, normalization)
+        finally:
+            self.model.early_exchange_hook = hook
+            if self.optim is not None:
+                self.optim._early_done = early_done
         torch.cuda.current_stream(self.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         l0 = _lib.lib.vmmt_launch_count()

@@ -497,9 +497,9 @@ class RowMLPFn(Function):
         dev = xs[0].device
         dys = [torch.zeros_like(y) if d is None else d.contiguous() for d, y in zip(dys, ys)]
         # layer 2: dh_p = (dy_p * act'(y_p)) W2_p; the transformed dy_p (= d pre-activation) is kept for dW2 / db2
-        dpre2 = [torch.empty(M, N2, device=dev, dtype=torch.float32) for _ in range(nh)]
+        dpre2 = [dy if a == ACT_NONE else torch.empty(M, N2, device=dev, dtype=torch.float32) for dy, a in zip(dys, acts)]
         dhs = [torch.empty(M, N1, device=dev, dtype=torch.float32) for _ in range(nh)]
-        rowlin([_rl_prob([dy], W2, None, dh, y=(y if a != ACT_NONE else None), yact=a, xt_out=dp)
+        rowlin([_rl_prob([dy], W2, None, dh, y=(y if a != ACT_NONE else None), yact=a, xt_out=(dp if a != ACT_NONE else None))
                 for (_, _, W2, _), dy, dh, y, a, dp in zip(heads, dys, dhs, ys, acts, dpre2)],
                M, N1, N2, transposed=True)
         # layer 1: dx = sum_p (dh_p * relu'(h_p)) W1_p over the column range some input needs
@@ -767,6 +767,23 @@ class MaskedMeanFn(Function):
         return dx, None
 
 
+_dropout_log = [None]
+
+
+def set_dropout_log(sink):
+    """Parity tests: ``sink`` (a list) receives (shape, p, seed, offset) of every dropout call, in call order, so that the
+    very masks the kernels drew can be regenerated (``dropout_mask``) and injected into the oracle."""
+    _dropout_log[0] = sink
+
+
+def dropout_mask(shape, p, seed, offset):
+    """The scaled keep-mask (0 or 1/(1-p)) the dropout kernel draws for (seed, offset) at the current step base."""
+    ones = torch.ones(*shape, device=torch.device("cuda", torch.cuda.current_device()), dtype=torch.float32)
+    m = torch.empty_like(ones)
+    L.call("vmmt_dropout", fptr(ones), fptr(m), ones.numel(), float(p), seed, offset, _base_ptr(), stream())
+    return m
+
+
 class DropoutFn(Function):
     """Inverted dropout with an in-kernel Philox mask, regenerated (not stored) in backward."""
 
@@ -775,6 +792,8 @@ class DropoutFn(Function):
         x = x.contiguous()
         y = torch.empty_like(x)
         ctx.p, ctx.seed, ctx.offset = p, _seed_state["seed"], _next_offset()
+        if _dropout_log[0] is not None:
+            _dropout_log[0].append((tuple(x.shape), p, ctx.seed, ctx.offset))
         L.call("vmmt_dropout", fptr(x), fptr(y), x.numel(), p, ctx.seed, ctx.offset, _base_ptr(), stream())
         return y
 
