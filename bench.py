@@ -797,7 +797,7 @@ def roofline_generator(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
     W, b = model.generator[0].weight, model.generator[0].bias
     lse = torch.empty(M, device=dev)
     stats = torch.zeros(3, device=dev)
-    wsb = _lib.lib.vmmt_generator_workspace_bytes(M, V)
+    wsb = _lib.lib.vmmt_generator_workspace_bytes(M, H, V)
     ws = torch.empty(wsb // 4, device=dev)
     flush = torch.empty(64 * 1024 * 1024, device=dev)           # 256 MB > L2
 

@@ -56,6 +56,14 @@ int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, int64_t ldb1,
                    const float* B2, int64_t ldb2, int K2, float* C, int64_t ldc, int M, int N, const float* bias, int act,
                    int flags, void* stream);
 
+/* bf16 variant (BASELINE configs[1] "fp32 and bf16"): dst[r, 0..ld_dst) = bf16(src[r, 0..cols)), zero padded to a pitch of a
+ * multiple of 8 elements; vmmt_gemm_bf16 = vmmt_gemm's contract on such bf16 operands (tcgen05.mma.kind::f16, fp32
+ * accumulate in tensor memory, fp32 output).  With VMMT_F_BF16 the generator entry points cast x and W into their
+ * workspace themselves (the two products with the fp32 softmax gradient stay TF32). */
+int vmmt_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int cols, void* stream);
+int vmmt_gemm_bf16(const void* A, int64_t lda, int a_kmajor, const void* B, int64_t ldb, int b_kmajor, float* C, int64_t ldc,
+                   int M, int N, int K, const float* bias, int act, int accumulate, int flags, void* stream);
+
 /* Embedding gather / dense scatter-add (Embeddings.py:169-188; nn.Embedding padding_idx row gets no grad). */
 int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int E, float* out, void* stream);
 int vmmt_embedding_bwd(const int64_t* idx, int64_t n, const float* dout, int E, int64_t pad_idx,
@@ -188,7 +196,7 @@ int vmmt_image_loss_bwd(const float* loc, const float* v, const float* rowstats,
                         int B, int D, void* stream);
 
 /* ---- generator + criterion (ModelConstructor.py:582-585; VILoss.py:228,243,515-531) */
-size_t vmmt_generator_workspace_bytes(int M, int V);
+size_t vmmt_generator_workspace_bytes(int M, int H, int V);
 int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b, const int64_t* target,
                            int64_t pad_idx, int M, int H, int V, float* lse /*[M]*/,
                            float* stats3 /*{nll_sum, n_words, n_correct}*/, void* workspace,

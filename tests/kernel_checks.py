@@ -365,5 +365,43 @@ def check_rowmlp(tol=1e-5):
     return out
 
 
+def check_gemm_bf16(tol=6e-3):
+    """bf16 variant (ops.set_gemm_mode(2)): vmmt_cast_bf16 + vmmt_gemm_bf16 (tcgen05.mma.kind::f16 on bf16 operands, fp32
+    accumulate) in all four operand-major combinations (forward, dgrad, wgrad forms), epilogues and accumulate modes,
+    against fp64 products of the bf16-ROUNDED operands (tight: only accumulation order differs) and of the unrounded
+    ones (the bf16 operand-rounding budget)."""
+    from variational_mmt_b200 import ops
+    out = []
+    assert ops.get_gemm_mode() == 2
+    rb = lambda t: t.to(torch.bfloat16).double()
+    for (M, N, K) in [(1240, 2000, 500), (256, 512, 1024), (77, 130, 52), (2000, 500, 1240), (1240, 10000, 500)]:
+        for ak, bk in [(True, True), (True, False), (False, False), (False, True)]:
+            a = _r(M, K, seed=1) if ak else _r(K, M, seed=1)
+            b = _r(N, K, seed=2) if bk else _r(K, N, seed=2)
+            bias = _r(N, seed=3)
+            A = a if ak else a.t()
+            B = b.t() if bk else b
+            c = torch.empty(M, N, device=DEV)
+            ops.gemm(a, b, c, M, N, K, a_kmajor=ak, b_kmajor=bk, bias=bias)
+            out.append((f"gemm_bf16 {M}x{N}x{K} a_k={int(ak)} b_k={int(bk)} vs rounded operands",
+                        _rel(c, rb(A) @ rb(B) + bias.double()), 2e-5))
+            out.append((f"gemm_bf16 {M}x{N}x{K} a_k={int(ak)} b_k={int(bk)} vs fp64", _rel(c, A.double() @ B.double() + bias.double()), tol))
+    M, N, K = 130, 96, 200
+    a, b, bias = _r(M, K, seed=4), _r(N, 2 * K, seed=5), _r(N, seed=6)
+    bv = b[:, K:]
+    c0 = _r(M, N, seed=7)
+    c = c0.clone()
+    ops.gemm(a, bv, c, M, N, K, act=2, accumulate=2)
+    out.append(("gemm_bf16 accumulate=2 tanh strided-B", _rel(c, torch.tanh(c0.double() + rb(a) @ rb(bv).t())), 2e-5))
+    c = c0.clone()
+    ops.gemm(a, bv, c, M, N, K, accumulate=1)
+    out.append(("gemm_bf16 accumulate=1", _rel(c, c0.double() + rb(a) @ rb(bv).t()), 2e-5))
+    a1, a2, w = _r(1250, 500, seed=8), _r(1250, 500, seed=9), _r(500, 1000, seed=10)
+    c = torch.empty(1250, 500, device=DEV)
+    ops.gemm_dual(a1, w[:, :500], a2, w[:, 500:], c, 1250, 500, 500, 500, act=2)
+    out.append(("gemm_dual bf16 tanh", _rel(c, torch.tanh(rb(torch.cat([a1, a2], 1)) @ rb(w).t())), 2e-5))
+    return out
+
+
 ALL = [("gemm", check_gemm), ("lstm", check_lstm), ("attention", check_attention), ("small_ops", check_small_ops),
        ("loss", check_loss), ("optim", check_optim), ("rowmlp", check_rowmlp)]

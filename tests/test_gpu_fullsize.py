@@ -28,7 +28,7 @@ def test_generator_nll_cfg5_shape_matches_torch(cuda_device):
     tgt[::7] = pad                                                    # ignored positions
     lse = torch.empty(M, device=dev)
     stats = torch.zeros(3, device=dev)
-    wsb = int(L.lib.vmmt_generator_workspace_bytes(M, V))
+    wsb = int(L.lib.vmmt_generator_workspace_bytes(M, H, V))
     ws = torch.empty(wsb // 4, device=dev)
     L.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), pad, M, H, V, fptr(lse), fptr(stats), fptr(ws),
            wsb, 0, stream())

@@ -40,3 +40,14 @@ def test_image_feature_table_gather(cuda_device):
     for idx in ([0], [776, 0, 5, 5, 123], rng.randint(0, 777, 40).tolist()):
         got = table.gather(torch.as_tensor(idx, dtype=torch.int64)).cpu().numpy()
         assert np.array_equal(got, feats[np.asarray(idx)])            # bit-exact: a copy
+
+
+def test_gemm_bf16_variant(cuda_device):
+    """The bf16 operand variant of the tcgen05 GEMM (BASELINE configs[1] "fp32 and bf16"; kernel_checks.check_gemm_bf16)."""
+    from variational_mmt_b200 import ops
+    ops.set_gemm_mode(2)
+    try:
+        bad = [(l, e, t) for l, e, t in kc.check_gemm_bf16() if not e <= t]
+    finally:
+        ops.set_gemm_mode(0)
+    assert not bad, "\n".join(f"{l}: err {e:.3e} > tol {t:.1e}" for l, e, t in bad)

@@ -13,7 +13,7 @@ b = (torch.rand(V, device=dev) - 0.5) * 0.2
 tgt = torch.randint(4, V, (M,), device=dev)
 lse = torch.empty(M, device=dev)
 stats = torch.zeros(3, device=dev)
-wsb = _lib.lib.vmmt_generator_workspace_bytes(M, V)
+wsb = _lib.lib.vmmt_generator_workspace_bytes(M, H, V)
 ws = torch.empty(wsb // 4, device=dev)
 for _ in range(3):
     _lib.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), 1, M, H, V, fptr(lse), fptr(stats),

@@ -282,6 +282,7 @@ class Optim(object):
         self._step += 1
         self._adam_t += 1
         ops.join_side()
+        ops.weights_changed()                # bf16 variant: cached casts of the parameters are stale after this update
         if self.decay_method == "noam":
             self._set_rate(self.original_lr * (self.model_size ** (-0.5) *
                            min(self._step ** (-0.5), self._step * self.warmup_steps ** (-1.5))))

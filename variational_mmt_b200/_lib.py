@@ -52,6 +52,8 @@ SIGNATURES = {
     "vmmt_launch_count": (C.c_ulonglong, []),
     "vmmt_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, I, P]),
     "vmmt_gemm_dual": (I, [P, L, P, L, I, P, L, P, L, I, P, L, I, I, P, I, I, P]),
+    "vmmt_cast_bf16": (I, [P, L, P, L, I, I, P]),
+    "vmmt_gemm_bf16": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, I, P]),
     "vmmt_embedding_fwd": (I, [P, L, P, I, P, P]),
     "vmmt_embedding_bwd": (I, [P, L, P, I, L, P, P]),
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
@@ -77,7 +79,7 @@ SIGNATURES = {
     "vmmt_gate_bwd": (I, [P, P, P, P, P, P, I, I, P]),
     "vmmt_image_loss_fwd": (I, [P, P, P, P, I, I, P]),
     "vmmt_image_loss_bwd": (I, [P, P, P, P, P, F, I, I, I, P]),
-    "vmmt_generator_workspace_bytes": (SZ, [I, I]),
+    "vmmt_generator_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_generator_nll_fwd": (I, [P, P, P, P, L, I, I, I, P, P, P, SZ, I, P]),
     "vmmt_generator_nll_bwd": (I, [P, P, P, P, L, P, P, F, I, I, I, P, P, P, P, SZ, I, P]),
     "vmmt_generator_nll_wgrad": (I, [P, P, I, I, I, P, P, I, P]),

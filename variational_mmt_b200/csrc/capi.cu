@@ -55,6 +55,7 @@ extern "C" int vmmt_gemm(const float* A, int64_t lda, int a_kmajor, const float*
                          int act, int accumulate, int flags, void* stream) {
   VMMT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dims");
   VMMT_REQUIRE(A && B && C, "gemm: null operand");
+  flags &= ~VMMT_F_BF16;                 // fp32 operands here: bf16 contractions go through vmmt_gemm_bf16 on cast operands
   cudaStream_t s = (cudaStream_t)stream;
   static const bool log_calls = getenv("VMMT_GEMM_LOG") != nullptr;      // debugging: which path each shape takes
   if (log_calls)
@@ -77,6 +78,7 @@ extern "C" int vmmt_gemm_dual(const float* A1, int64_t lda1, const float* B1, in
                               int64_t ldc, int M, int N, const float* bias, int act, int flags, void* stream) {
   VMMT_REQUIRE(M >= 0 && N >= 0 && K1 >= 1 && K2 >= 1, "gemm_dual: bad dims");
   VMMT_REQUIRE(A1 && B1 && A2 && B2 && C, "gemm_dual: null operand");
+  flags &= ~VMMT_F_BF16;
   cudaStream_t s = (cudaStream_t)stream;
   if (!(flags & VMMT_F_EXACT) && vmmt_gemm_tc_eligible(A1, lda1, 1, B1, ldb1, 1, C, ldc, M, N, K1, flags) &&
       vmmt_gemm_tc_eligible(A2, lda2, 1, B2, ldb2, 1, C, ldc, M, N, K2, flags)) {

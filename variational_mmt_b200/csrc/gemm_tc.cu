@@ -16,7 +16,13 @@
 // dgrad and wgrad all run on the same kernel with no transposing copy: the UMMA descriptors and the
 // instruction descriptor's major bits select the layout.  Ragged M / N / K need no padding: TMA
 // zero-fills out-of-bounds box elements and the epilogue masks its stores.
+//
+// bf16 variant (BF = true; BASELINE configs[1] "fp32 and bf16"): the SAME kernel on bf16 operands -- a 128-byte swizzle row
+// holds 64 bf16 instead of 32 fp32 and one tcgen05.mma.kind::f16 consumes 16 of them (the same 32 bytes), so the shared
+// memory geometry, the ring, the TMEM accumulators (fp32) and every epilogue are unchanged; only the tensor maps' element
+// type / box, the instruction descriptor and the MN-major tile geometry (64-element rows, 8-row swizzle atoms) differ.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <mutex>
 #include <stdlib.h>
 #include <stdio.h>
@@ -26,8 +32,8 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                    // fp32 elements per stage along K = one 128-byte swizzle row
-constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction along K
+constexpr int BK = 32;                    // fp32 elements per stage along K = one 128-byte swizzle row (bf16: 64 elements)
+constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction along K (bf16: 16 elements)
 constexpr int EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr int A_STAGE_BYTES = BM * BK * 4;               // 16 KB
@@ -87,6 +93,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -382,7 +397,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmArgs& g, const CUten
 // GEN = true instantiates the generator epilogues (LSE / dlogits / top-K); they roughly double the register count, so the
 // plain GEMMs get their own instantiation (96 instead of 180 registers per thread: two 64-wide CTAs per SM, and room
 // for a recurrence CTA beside a weight-gradient CTA on the same SM).
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool GEN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool GEN, bool BF = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
@@ -398,8 +413,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull0 = bar0 + 16 * STAGES, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)STAGES * STAGE + epi_bytes() + 16 * STAGES + 32);
 
+  constexpr int BKE = BF ? 2 * BK : BK;          // ELEMENTS per k-block (one 128-byte row)
+  constexpr int MNE = BF ? 64 : 32;              // MN-major: elements per 128-byte row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb_total = (g.K + BK - 1) / BK;
+  const int nkb_total = (g.K + BKE - 1) / BKE;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + g.kb_per_split);
   const int nkb1 = kb1 - kb0;                            // k-blocks of the first operand pair per tile
@@ -468,30 +485,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t fb = full0 + 8 * s;
         const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
         const bool second = i >= nkb1;                             // k-blocks of the second operand pair follow the first
-        const int k = second ? (i - nkb1) * BK : (kb0 + i) * BK;
+        const int k = second ? (i - nkb1) * BKE : (kb0 + i) * BKE;
         const CUtensorMap* pa = second ? &tmA2 : &tmA;
         const CUtensorMap* pb = second ? &tmB2 : &tmB;
         if (leader) {
           mbar_expect_tx(fb, STAGE);
           if (!A_MN) {
-            tma_load_2d(sa, pa, k, m0, fb);                        // box {32 k, 128 rows}
+            tma_load_2d(sa, pa, k, m0, fb);                        // box {128 B of k, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), pa, m0 + 32 * j, k, fb);   // box {32 m, 32 k}
+            for (int j = 0; j < BM / MNE; ++j) tma_load_2d(sa + j * (BKE * 128), pa, m0 + MNE * j, k, fb);   // box {128 B of m, BKE k}
           }
           if (!B_MN) {
-            tma_load_2d(sb, pb, k, n0, fb);                        // box {32 k, BN rows}
+            tma_load_2d(sb, pb, k, n0, fb);                        // box {128 B of k, BN rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), pb, n0 + 32 * j, k, fb);
+            for (int j = 0; j < BN / MNE; ++j) tma_load_2d(sb + j * (BKE * 128), pb, n0 + MNE * j, k, fb);
           }
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+    // instruction descriptor: D=f32, A=B=tf32 (kind::tf32 format 2) or bf16 (kind::f16 format 1), majors, N>>3, M>>4
+    constexpr uint32_t FMT = BF ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
                            ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int it = 0, lt = 0;
     for (int lin = cta; lin < tiles_total; lin += ncta, ++lt) {
@@ -508,9 +526,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sa = base + s * STAGE, sb = sa + A_STAGE_BYTES;
 #pragma unroll
         for (int j = 0; j < BK / UMMA_K; ++j) {
-          const uint64_t ad = A_MN ? make_desc(sa + j * 1024, BK * 128, 512, 1) : make_desc(sa + j * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_desc(sb + j * 1024, BK * 128, 512, 1) : make_desc(sb + j * 32, 16, 1024);
-          if (leader) umma_tf32(tacc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          // MN-major, one instruction = 8 (tf32) / 16 (bf16) k-rows of 128 B: tf32 uses the 32-byte-atom swizzle (4-row
+          // atoms, SBO 512, layout type 1), bf16 the plain 128-byte swizzle (8-row atoms, SBO 1024, layout type 2); LBO is
+          // the distance between the 128-byte-wide MN groups of the tile
+          const uint64_t ad = A_MN ? (BF ? make_desc(sa + j * 2048, BKE * 128, 1024, 2) : make_desc(sa + j * 1024, BK * 128, 512, 1))
+                                   : make_desc(sa + j * 32, 16, 1024);
+          const uint64_t bd = B_MN ? (BF ? make_desc(sb + j * 2048, BKE * 128, 1024, 2) : make_desc(sb + j * 1024, BK * 128, 512, 1))
+                                   : make_desc(sb + j * 32, 16, 1024);
+          if (leader) {
+            if (BF) umma_bf16(tacc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+            else umma_tf32(tacc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          }
         }
         if (leader) umma_commit(empty0 + 8 * s);          // slot reusable once these MMAs have read it
         __syncwarp();
@@ -617,19 +643,21 @@ EncodeTiledFn get_encode() {
 
 // tensor map over a row-major fp32 matrix [outer, inner] with row stride ld (elements); box {32, box_rows}
 int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int64_t ld, int box_rows, bool mn_major,
-             bool plain_f32 = false) {
+             bool plain_f32 = false, bool bf16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     vmmt_set_error("gemm_tc: cuTensorMapEncodeTiled is unavailable");
     return VMMT_ELAUNCH;
   }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {bf16 ? 64u : 32u, (cuuint32_t)box_rows};          // 128 bytes of the inner dimension
   cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = enc(tm, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                      : (plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
+  const CUresult r = enc(tm, dt, 2, const_cast<float*>(p), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -642,9 +670,9 @@ int make_map(CUtensorMap* tm, const float* p, int64_t inner, int64_t outer, int6
 
 struct Maps { CUtensorMap a, b, c, a2, b2; };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool GEN = false>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool GEN = false, bool BF = false>
 int launch(const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
-  auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN, GEN>;
+  auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN, GEN, BF>;
   static bool attr_done = false;        // per instantiation
   constexpr size_t smem = smem_bytes(BN, STAGES);
   if (!attr_done) {
@@ -655,16 +683,16 @@ int launch(const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
   return vmmt_check_launch("gemm_tf32_kernel");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BF = false>
 int launch_major(bool a_mn, bool b_mn, const Maps& m, const GemmArgs& g, dim3 grid, cudaStream_t s) {
   if (g.epi_mode != 0) {                 // generator epilogues: x [M,H] and W [V,H] are both K-major
     if (a_mn || b_mn || BN != 128) return VMMT_EINVAL;
-    return launch<128, STAGES, false, false, true>(m, g, grid, s);
+    return launch<128, STAGES, false, false, true, BF>(m, g, grid, s);
   }
-  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(m, g, grid, s);
-  if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(m, g, grid, s);
-  if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(m, g, grid, s);
-  return launch<BN, STAGES, true, true>(m, g, grid, s);
+  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false, false, BF>(m, g, grid, s);
+  if (!a_mn && b_mn) return launch<BN, STAGES, false, true, false, BF>(m, g, grid, s);
+  if (a_mn && !b_mn) return launch<BN, STAGES, true, false, false, BF>(m, g, grid, s);
+  return launch<BN, STAGES, true, true, false, BF>(m, g, grid, s);
 }
 
 }  // namespace
@@ -703,11 +731,15 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
                       const VmmtGenEpi* epi, const VmmtGemmSecond* second, int flags, cudaStream_t s) {
   const bool a_mn = !a_kmajor, b_mn = !b_kmajor;
   const bool background = (flags & VMMT_F_BACKGROUND) != 0;
+  // VMMT_F_BF16 on this INTERNAL entry point: A / B (and the second pair) point to bf16 data, lda / ldb count bf16
+  // elements (vmmt_gemm_bf16 and the generator's bf16 path cast the fp32 tensors first)
+  const bool bf = (flags & VMMT_F_BF16) != 0;
+  const int bke = bf ? 2 * BK : BK;                            // elements per k-block
   const int nsm = vmmt_num_sms();
   const int tiles_m = ceil_div(M, BM);
-  const int nkb2 = second ? ceil_div(second->K2, BK) : 0;
+  const int nkb2 = second ? ceil_div(second->K2, bke) : 0;
   if (second && (a_mn || b_mn)) return VMMT_EINVAL;            // the second pair shares the K-major instantiation
-  const int nkb = ceil_div(K, BK) + nkb2;                       // k-blocks per output tile (cost model); split-K only without a second pair
+  const int nkb = ceil_div(K, bke) + nkb2;                       // k-blocks per output tile (cost model); split-K only without a second pair
   // (tile width, split-K) from a small cost model in SM cycles: a CTA costs a fixed prologue + epilogue plus
   // its k-blocks; 128-wide tiles run one CTA per SM (shared-memory-bandwidth bound, ~450 cycles per k-block),
   // 64-wide tiles two per SM; split-K needs a linear epilogue (an activation is applied by a finishing pass)
@@ -742,9 +774,9 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   int rc;
   // K-major operand [rows,K]: inner = K, outer = rows, box {32 k, tile rows}
   // MN-major operand [K,rows]: inner = rows, outer = K,  box {32 rows, 32 k}
-  rc = a_mn ? make_map(&ta, A, M, K, lda, BK, true) : make_map(&ta, A, K, M, lda, BM, false);
+  rc = a_mn ? make_map(&ta, A, M, K, lda, bke, true, false, bf) : make_map(&ta, A, K, M, lda, BM, false, false, bf);
   if (rc) return rc;
-  rc = b_mn ? make_map(&tb, B, N, K, ldb, BK, true) : make_map(&tb, B, K, N, ldb, BN, false);
+  rc = b_mn ? make_map(&tb, B, N, K, ldb, bke, true, false, bf) : make_map(&tb, B, K, N, ldb, BN, false, false, bf);
   if (rc) return rc;
   static int dbg = getenv("VMMT_GEMM_DBG") ? atoi(getenv("VMMT_GEMM_DBG")) : 0;
   // C through TMA (store / reduce-add) when its base and pitch are 16-byte aligned; else direct stores
@@ -761,9 +793,9 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   }
   Maps maps{ta, tb, tc, ta, tb};
   if (second) {
-    rc = make_map(&maps.a2, second->A2, second->K2, M, second->lda2, BM, false);
+    rc = make_map(&maps.a2, second->A2, second->K2, M, second->lda2, BM, false, false, bf);
     if (rc) return rc;
-    rc = make_map(&maps.b2, second->B2, second->K2, N, second->ldb2, BN, false);
+    rc = make_map(&maps.b2, second->B2, second->K2, N, second->ldb2, BN, false, false, bf);
     if (rc) return rc;
   }
   GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, tiles_m, ceil_div(N, BN), nkb2, nullptr,
@@ -815,7 +847,10 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
     }
   } dump{tracing, trace_buf, grid, s, BN};
   static const int deep = getenv("VMMT_GEMM_DEEP") ? atoi(getenv("VMMT_GEMM_DEEP")) : 0;
-  if (deep)
+  if (bf)
+    rc = (BN == 128) ? launch_major<128, 5, true>(a_mn, b_mn, maps, g, grid, s)
+                     : launch_major<64, 3, true>(a_mn, b_mn, maps, g, grid, s);
+  else if (deep)
     rc = (BN == 128) ? launch_major<128, 6>(a_mn, b_mn, maps, g, grid, s)
                      : launch_major<64, 8>(a_mn, b_mn, maps, g, grid, s);
   else
@@ -828,4 +863,53 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
     return vmmt_check_launch("gemm_tc_finish_act");
   }
   return VMMT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------- bf16 variant
+namespace {
+// dst[r, 0..ld_dst) = bf16(src[r, 0..cols)), zero padded to ld_dst (a multiple of 8: 16-byte row pitch for the TMA)
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
+                                 int64_t ld_dst, int rows, int cols) {
+  const int64_t per = ld_dst / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * per) return;
+  const int r = (int)(i / per), c0 = (int)(i % per) * 8;
+  const float* s = src + (int64_t)r * ld_src + c0;
+  float v[8];
+  if (c0 + 8 <= cols && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? __ldg(s + j) : 0.f;
+  }
+  __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(dst + (int64_t)r * ld_dst + c0) = *reinterpret_cast<const uint4*>(o);
+}
+}  // namespace
+
+extern "C" int vmmt_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int cols, void* stream) {
+  VMMT_REQUIRE(src && dst && rows >= 0 && cols >= 0, "cast_bf16: bad arguments");
+  VMMT_REQUIRE(ld_dst % 8 == 0 && ld_dst >= cols && ((uintptr_t)dst & 15) == 0,
+               "cast_bf16: the destination pitch must be a multiple of 8 elements >= cols and the base 16-byte aligned");
+  if (rows == 0 || cols == 0) return VMMT_OK;
+  const int64_t n = (int64_t)rows * (ld_dst / 8);
+  cast_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+  return vmmt_check_launch("cast_bf16_kernel");
+}
+
+// C[M,N] (fp32) = act(op(A) op(B) + bias) (+C) on bf16 operands (fp32 accumulate in tensor memory); same contract as
+// vmmt_gemm, A / B are bf16 matrices with 16-byte aligned bases and pitches of a multiple of 8 elements.
+extern "C" int vmmt_gemm_bf16(const void* A, int64_t lda, int a_kmajor, const void* B, int64_t ldb, int b_kmajor, float* C,
+                              int64_t ldc, int M, int N, int K, const float* bias, int act, int accumulate, int flags,
+                              void* stream) {
+  VMMT_REQUIRE(M >= 1 && N >= 1 && K >= 1 && A && B && C, "gemm_bf16: bad arguments");
+  VMMT_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && (lda & 7) == 0 && (ldb & 7) == 0,
+               "gemm_bf16: operands need 16-byte aligned bases and pitches of a multiple of 8 elements");
+  return vmmt_gemm_tc_dual(reinterpret_cast<const float*>(A), lda, a_kmajor, reinterpret_cast<const float*>(B), ldb, b_kmajor,
+                           C, ldc, M, N, K, bias, act, accumulate, nullptr, nullptr, flags | VMMT_F_BF16,
+                           (cudaStream_t)stream);
 }

@@ -139,15 +139,35 @@ extern "C" int vmmt_gemm(const float*, int64_t, int, const float*, int64_t, int,
 extern "C" int vmmt_generator_nll_wgrad(const float* x, const void* workspace, int M, int H, int V, float* dW,
                                         float* db, int flags, void* stream);
 
-extern "C" size_t vmmt_generator_workspace_bytes(int M, int V) {
-  return ((size_t)M * V + (size_t)M * 4) * sizeof(float);
+extern "C" int vmmt_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int cols, void* stream);
+
+// [M,V] fp32 logits / dlogits | [M,4] row statistics | bf16 copies of x [M,Hp] and W [V,Hp] (VMMT_F_BF16), Hp = H rounded to 8
+static size_t gen_f32_floats(int M, int V) { return (((size_t)M * V + (size_t)M * 4) + 3) / 4 * 4; }
+extern "C" size_t vmmt_generator_workspace_bytes(int M, int H, int V) {
+  const size_t hp = (size_t)(H + 7) / 8 * 8;
+  return gen_f32_floats(M, V) * sizeof(float) + ((size_t)M + (size_t)V) * hp * 2 + 32;
+}
+// bf16 variant: x and W are cast into the tail of the workspace; returns the operand pointers / pitch to contract
+static int gen_bf16_operands(const float* x, const float* W, int M, int H, int V, void* workspace, const float** xo,
+                             const float** wo, int64_t* ld, void* stream) {
+  const int64_t hp = (int64_t)(H + 7) / 8 * 8;
+  char* base = reinterpret_cast<char*>(workspace) + gen_f32_floats(M, V) * sizeof(float);
+  base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
+  void* xb = base;
+  void* wb = base + (size_t)M * hp * 2;
+  int rc = vmmt_cast_bf16(x, H, xb, hp, M, H, stream);
+  if (rc) return rc;
+  rc = vmmt_cast_bf16(W, H, wb, hp, V, H, stream);
+  if (rc) return rc;
+  *xo = reinterpret_cast<const float*>(xb); *wo = reinterpret_cast<const float*>(wb); *ld = hp;
+  return VMMT_OK;
 }
 
 extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const float* b,
                                       const int64_t* target, int64_t pad_idx, int M, int H, int V,
                                       float* lse, float* stats3, void* workspace,
                                       size_t workspace_bytes, int flags, void* stream) {
-  if (workspace_bytes < vmmt_generator_workspace_bytes(M, V)) {
+  if (workspace_bytes < vmmt_generator_workspace_bytes(M, H, V)) {
     vmmt_set_error("generator_nll_fwd: workspace too small");
     return VMMT_EWORKSPACE;
   }
@@ -162,7 +182,13 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
     float* part = logits;                                  // ntile * M * 4 floats  <<  M * V
     float* tgt_logit = part + (size_t)ntile * M * 4;
     VmmtGenEpi epi{1, part, tgt_logit, target, nullptr, nullptr, 1.0f, (long long)pad_idx};
-    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, (cudaStream_t)stream);
+    const float *xo = x, *wo = W;
+    int64_t ldo = H;
+    if (flags & VMMT_F_BF16) {                             // bf16 operands: cast into the tail of the workspace
+      rc = gen_bf16_operands(x, W, M, H, V, workspace, &xo, &wo, &ldo, stream);
+      if (rc) return rc;
+    }
+    rc = vmmt_gemm_tc_ex(xo, ldo, 1, wo, ldo, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, (cudaStream_t)stream);
     if (rc) return rc;
     lse_combine_kernel<<<ceil_div(M, 4), 128, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(part), tgt_logit, target, pad_idx, M, ntile, lse, rowstat);
@@ -171,7 +197,7 @@ extern "C" int vmmt_generator_nll_fwd(const float* x, const float* W, const floa
     reduce_rowstat_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowstat, M, stats3);
     return vmmt_check_launch("reduce_rowstat");
   }
-  rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, flags, stream);
+  rc = vmmt_gemm(x, H, 1, W, H, 1, logits, V, M, V, H, b, VMMT_ACT_NONE, 0, flags & ~VMMT_F_BF16, stream);
   if (rc) return rc;
   row_lse_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, target, pad_idx, lse, rowstat, V);
   rc = vmmt_check_launch("row_lse");
@@ -185,7 +211,7 @@ extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const floa
                                       const float* gscale, float scale, int M, int H, int V, float* dx, float* dW,
                                       float* db, void* workspace, size_t workspace_bytes, int flags,
                                       void* stream) {
-  if (workspace_bytes < vmmt_generator_workspace_bytes(M, V)) {
+  if (workspace_bytes < vmmt_generator_workspace_bytes(M, H, V)) {
     vmmt_set_error("generator_nll_bwd: workspace too small");
     return VMMT_EWORKSPACE;
   }
@@ -196,8 +222,14 @@ extern "C" int vmmt_generator_nll_bwd(const float* x, const float* W, const floa
   if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_GEN_UNFUSED") && (V & 3) == 0 &&
       vmmt_gemm_tc_eligible(x, H, 1, W, H, 1, dl, V, M, V, H, flags)) {
     VmmtGenEpi epi{2, nullptr, nullptr, target, lse, gscale, scale, (long long)pad_idx};
-    rc = vmmt_gemm_tc_ex(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, s);
+    const float *xo = x, *wo = W;
+    int64_t ldo = H;
+    rc = VMMT_OK;
+    if (flags & VMMT_F_BF16) rc = gen_bf16_operands(x, W, M, H, V, workspace, &xo, &wo, &ldo, stream);   // the recompute matches the forward
+    if (rc == VMMT_OK) rc = vmmt_gemm_tc_ex(xo, ldo, 1, wo, ldo, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, s);
   }
+  // the two gradient products below contract the fp32 softmax gradient: they stay on the TF32 path in the bf16 variant
+  flags &= ~VMMT_F_BF16;
   if (rc != VMMT_OK) {
     rc = vmmt_gemm(x, H, 1, W, H, 1, dl, V, M, V, H, b, VMMT_ACT_NONE, 0, flags, stream);
     if (rc) return rc;
@@ -264,5 +296,6 @@ extern "C" int vmmt_generator_topk(const float* x, const float* W, const float* 
   epi.topk = K;
   epi.tile_lse = tile_lse;
   epi.tile_cand = tile_cand;
-  return vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags, (cudaStream_t)stream);
+  return vmmt_gemm_tc_ex(x, H, 1, W, H, 1, nullptr, V, M, V, H, b, VMMT_ACT_NONE, 0, &epi, flags & ~VMMT_F_BF16,
+                         (cudaStream_t)stream);
 }

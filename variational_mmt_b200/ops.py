@@ -32,6 +32,7 @@ def get_gemm_mode():
 
 
 def flags():
+    """The per-call `flags` of the C ABI for the current host-side mode."""
     m = _mode["gemm"]
     return (L.F_EXACT if m == 1 else L.F_BF16 if m == 2 else 0) | (L.F_BACKGROUND if _mode["background"] else 0) | \
         (L.F_NO_SPLITK if _mode["invariant"] else 0)
@@ -86,6 +87,7 @@ def _base_ptr():
 def begin_step():
     """Restart the per-step call index (call at the top of a step that ends with advance_rng())."""
     _seed_state["offset"] = 0
+    _bf16["cache"].clear()
 
 
 def advance_rng():
@@ -273,9 +275,47 @@ def grad_buf(p):
     return p.grad
 
 
+# ---- bf16 variant (set_gemm_mode(2)): operands are cast to bf16 (pitch padded to 8 elements) and contracted by the same
+# tcgen05 kernel with kind::f16 MMAs.  Casts of PARAMETERS (views of the flat parameter buffer) are cached until the
+# weights change (Optim.step) or a new step begins (begin_step: a captured graph must contain its own casts).
+_bf16 = {"version": 0, "cache": {}}
+
+
+def weights_changed():
+    _bf16["version"] += 1
+    _bf16["cache"].clear()
+
+
+def _as_bf16(t, rows, cols):
+    """bf16 copy [rows, cols padded to 8] of the 2-D fp32 view `t` (unit inner stride)."""
+    from .flat import _OWNERS
+    is_param = t.untyped_storage().data_ptr() in _OWNERS              # a view of a flat parameter buffer
+    key = (t.data_ptr(), rows, cols, t.stride(0)) if is_param else None
+    if key is not None:
+        hit = _bf16["cache"].get(key)
+        if hit is not None:
+            return hit
+    ld = (cols + 7) // 8 * 8
+    dst = torch.empty(rows, ld, device=t.device, dtype=torch.bfloat16)
+    L.call("vmmt_cast_bf16", fptr(t), t.stride(0), dst.data_ptr(), ld, rows, cols, stream())
+    if key is not None:
+        _bf16["cache"][key] = dst
+    return dst
+
+
+def _bf16_ok(a, b, M, N, K):
+    return (_mode["gemm"] == 2 and N >= 64 and K >= 16 and M * N * K >= 64 * 64 * 64 and a.dtype == torch.float32)
+
+
 def gemm(a, b, out, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, accumulate=0):
     """out[M,N] = act(op(a) op(b) + bias) (+out).  a, b, out: 2-D views with unit inner stride."""
     assert a.stride(-1) == 1 and b.stride(-1) == 1 and out.stride(-1) == 1
+    if _bf16_ok(a, b, M, N, K):
+        ab = _as_bf16(a, M if a_kmajor else K, K if a_kmajor else M)
+        bb = _as_bf16(b, N if b_kmajor else K, K if b_kmajor else N)
+        L.call("vmmt_gemm_bf16", ab.data_ptr(), ab.stride(0), int(a_kmajor), bb.data_ptr(), bb.stride(0), int(b_kmajor),
+               fptr(out), out.stride(0), M, N, K, fptr(bias), act, int(accumulate), flags() & ~L.F_BF16, stream())
+        return out
     L.call("vmmt_gemm", fptr(a), a.stride(0), int(a_kmajor), fptr(b), b.stride(0), int(b_kmajor),
            fptr(out), out.stride(0), M, N, K, fptr(bias), act, int(accumulate), flags(), stream())
     return out
@@ -284,6 +324,9 @@ def gemm(a, b, out, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NO
 def gemm_dual(a1, b1, a2, b2, out, M, N, K1, K2, bias=None, act=ACT_NONE):
     """out[M,N] = act(a1 b1^T + a2 b2^T + bias) in one launch (all operands [rows, K] with unit inner stride)."""
     assert a1.stride(-1) == 1 and b1.stride(-1) == 1 and a2.stride(-1) == 1 and b2.stride(-1) == 1 and out.stride(-1) == 1
+    if _bf16_ok(a1, b1, M, N, K1) and _bf16_ok(a2, b2, M, N, K2):
+        gemm(a1, b1, out, M, N, K1, bias=bias)                      # two accumulating launches in the bf16 variant
+        return gemm(a2, b2, out, M, N, K2, act=act, accumulate=(1 if act == ACT_NONE else 2))
     L.call("vmmt_gemm_dual", fptr(a1), a1.stride(0), fptr(b1), b1.stride(0), K1, fptr(a2), a2.stride(0), fptr(b2),
            b2.stride(0), K2, fptr(out), out.stride(0), M, N, fptr(bias), act, flags(), stream())
     return out
@@ -873,7 +916,7 @@ class VILossFn(Function):
         V = gen_w.shape[0]
         stats = torch.zeros(8, device=dev, dtype=torch.float32)
         lse = torch.empty(M, device=dev, dtype=torch.float32)
-        wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
+        wsb = L.lib.vmmt_generator_workspace_bytes(M, H, V)
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
         mu_q, sd_q = mu_q.contiguous(), sd_q.contiguous()
         B, Z = mu_q.shape
@@ -929,7 +972,7 @@ class VILossFn(Function):
             L.call("vmmt_image_loss_bwd", fptr(img_loc), fptr(img_v), fptr(rowstats), fptr(dloc), fptr(gs), 1.0,
                    int(cfg.get("legacy_image_grad", True)), B, D, stream())
         dx = torch.empty(M, H, device=dev, dtype=torch.float32)
-        wsb = L.lib.vmmt_generator_workspace_bytes(M, V)
+        wsb = L.lib.vmmt_generator_workspace_bytes(M, H, V)
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
         L.call("vmmt_generator_nll_bwd", fptr(out2d), fptr(ctx.gen_w), fptr(ctx.gen_b), ptr(target),
                cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), None, None, fptr(ws), wsb, flags(), stream())
