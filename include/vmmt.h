@@ -253,16 +253,21 @@ int64_t vmmt_peer_slice(int64_t n, int world, int rank, int64_t* lo, int64_t* hi
 /* The two halves of the step over a sub-range [begin, begin + n) of the flat buffers, so that a step can exchange the
  * gradients that are final early (generator, latent / image networks) BESIDE the rest of the backward pass (phase 1)
  * and the remainder at the end (phase 0); the clip norm is the sum over `nphase` published slot arrays. */
-int vmmt_peer_reduce_scatter(void* const* segments, size_t grad_off, int rank, int world, int64_t begin, int64_t n,
-                             float* gsum, int phase, void* workspace, void* stream);
-int vmmt_peer_adam_allgather(void* const* segments, size_t param_off, int rank, int world, int64_t begin, int64_t n,
-                             const float* gsum, float* exp_avg, float* exp_avg_sq, float* sqnorm_out, int nphase,
+/* mc_base: the segments' MULTICAST address (all N segments bound to one cuMulticast object, e.g. by torch's symmetric
+ * memory) or NULL.  With it the reduce-scatter is multimem.ld_reduce (the NVSwitch adds the N ranks' values in flight)
+ * and the all-gather is multimem.st (one store replicated by the switch): 4 B/param/N per rank each way instead of
+ * (N-1)/N * 4 B/param of P2P loads / stores. */
+int vmmt_peer_reduce_scatter(void* const* segments, void* mc_base, size_t grad_off, int rank, int world, int64_t begin,
+                             int64_t n, float* gsum, int phase, void* workspace, void* stream);
+int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, size_t param_off, int rank, int world, int64_t begin,
+                             int64_t n, const float* gsum, float* exp_avg, float* exp_avg_sq, float* sqnorm_out, int nphase,
                              float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                              int barrier_before, int barrier_after, void* stream);
 /* barrier -> reduce-scatter (P2P loads, rank-ordered sum) + ||g||^2 share -> barrier -> clip + Adam on the slice,
  * new parameters stored into all N parameter buffers (P2P stores) -> barrier.  sqnorm_out (optional) receives the
  * squared global norm of the summed gradient.  No NCCL, no host synchronisation, CUDA-graph capturable. */
-int vmmt_peer_adam_step(void* const* segments, size_t param_off, size_t grad_off, int rank, int world, int64_t n,
+int vmmt_peer_adam_step(void* const* segments, void* mc_base, size_t param_off, size_t grad_off, int rank, int world,
+                        int64_t n,
                         float* gsum, float* exp_avg, float* exp_avg_sq, float* sqnorm_out, float max_norm, float lr,
                         float beta1, float beta2, float eps, int64_t step, void* workspace, void* stream);
 

@@ -245,7 +245,7 @@ class Optim(object):
             xs.wait_stream(st)
         n = self.flat.numel()
         with torch.cuda.stream(xs):
-            L.call("vmmt_peer_reduce_scatter", pe.segments, pe.grad_off, pe.rank, pe.world, e["begin"], n - e["begin"],
+            L.call("vmmt_peer_reduce_scatter", pe.segments, pe.mc_base, pe.grad_off, pe.rank, pe.world, e["begin"], n - e["begin"],
                    fptr(e["gsum_a"]), 1, fptr(e["ws_a"]), stream())
         self._early_done = True
 
@@ -256,12 +256,14 @@ class Optim(object):
 
     @property
     def exchange_in_use(self):
+        how = "nvls multimem.ld_reduce reduce-scatter + sharded clip/Adam + multimem.st all-gather" \
+            if (self.peer is not None and self.peer.mc_base) else "nvlink p2p reduce-scatter + sharded clip/Adam + all-gather"
         if self.peer is not None and self._early is not None:
-            return ("nvlink p2p reduce-scatter + sharded clip/Adam + all-gather (csrc/peer.cu); tail of the buffer "
-                    "(latent / image networks, generator: %.0f%%) reduce-scattered beside the encoder backward"
+            return (how + " (csrc/peer.cu); tail of the buffer (latent / image networks, generator: %.0f%%) "
+                    "reduce-scattered beside the encoder backward"
                     % (100.0 * (self.flat.numel() - self._early["begin"]) / self.flat.numel()))
         if self.peer is not None:
-            return "nvlink p2p reduce-scatter + sharded clip/Adam + all-gather (csrc/peer.cu)"
+            return how + " (csrc/peer.cu)"
         return "nccl all-reduce + replicated clip/Adam" if distributed.is_active() else "single rank"
 
     def _set_rate(self, lr):
@@ -296,16 +298,16 @@ class Optim(object):
             self._early_done = False
             b0, sm = e["begin"], stream()
             hyp = (max_norm, float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._adam_t)
-            L.call("vmmt_peer_reduce_scatter", pe.segments, pe.grad_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]), 0,
+            L.call("vmmt_peer_reduce_scatter", pe.segments, pe.mc_base, pe.grad_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]), 0,
                    fptr(self._pws), sm)
-            L.call("vmmt_peer_adam_allgather", pe.segments, pe.param_off, pe.rank, pe.world, b0, n - b0, fptr(e["gsum_a"]),
+            L.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, b0, n - b0, fptr(e["gsum_a"]),
                    fptr(e["m_a"]), fptr(e["v_a"]), fptr(self._sq), 2, *hyp, 1, 0, sm)
-            L.call("vmmt_peer_adam_allgather", pe.segments, pe.param_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]),
+            L.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]),
                    fptr(e["m_b"]), fptr(e["v_b"]), None, 2, *hyp, 0, 1, sm)
             return
         if self.peer is not None:
             pe = self.peer
-            L.call("vmmt_peer_adam_step", pe.segments, pe.param_off, pe.grad_off, pe.rank, pe.world, n,
+            L.call("vmmt_peer_adam_step", pe.segments, pe.mc_base, pe.param_off, pe.grad_off, pe.rank, pe.world, n,
                    fptr(self._gsum), fptr(self.exp_avg), fptr(self.exp_avg_sq), fptr(self._sq), max_norm,
                    float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._adam_t, fptr(self._pws),
                    stream())

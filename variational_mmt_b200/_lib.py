@@ -100,9 +100,9 @@ SIGNATURES = {
     "vmmt_peer_barrier": (I, [P, I, I, P]),
     "vmmt_peer_adam_workspace_bytes": (SZ, []),
     "vmmt_peer_slice": (L, [L, I, I, C.POINTER(L), C.POINTER(L)]),
-    "vmmt_peer_reduce_scatter": (I, [P, SZ, I, I, L, L, P, I, P, P]),
-    "vmmt_peer_adam_allgather": (I, [P, SZ, I, I, L, L, P, P, P, P, I, F, F, F, F, F, L, I, I, P]),
-    "vmmt_peer_adam_step": (I, [P, SZ, SZ, I, I, L, P, P, P, P, F, F, F, F, F, L, P, P]),
+    "vmmt_peer_reduce_scatter": (I, [P, P, SZ, I, I, L, L, P, I, P, P]),
+    "vmmt_peer_adam_allgather": (I, [P, P, SZ, I, I, L, L, P, P, P, P, I, F, F, F, F, F, L, I, I, P]),
+    "vmmt_peer_adam_step": (I, [P, P, SZ, SZ, I, I, L, P, P, P, P, F, F, F, F, F, L, P, P]),
     "vmmt_beam_advance": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
     "vmmt_beam_advance_topk": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
     "vmmt_beam_record": (I, [P, P, P, L, P]),

@@ -17,6 +17,11 @@
 // Per rank and step NVLink carries (N-1)/N * 4 B/param in and the same out -- the reduce-scatter +
 // all-gather lower bound -- and the Adam pass touches 1/N of the optimiser state.
 //
+// NVLS (default when the host maps the segments through torch's symmetric memory: cuMem + cuMulticast): steps 2 and 4
+// use multimem.ld_reduce / multimem.st on the segment's multicast address -- the NVSwitch forms the sum of the N
+// gradient float4s and replicates the parameter store, a rank moves 4 B/param/N each way.  The P2P kernels below stay
+// as the path for hosts without multicast support.
+//
 // Peer memory is plain cudaMalloc memory exported with cudaIpcGetMemHandle (one process per GPU);
 // the 64-byte handles travel over whatever control plane the host has (torch.distributed object
 // all-gather in variational_mmt_b200/distributed.py).  Cross-GPU barriers are flag words in that
@@ -148,6 +153,74 @@ peer_adam_allgather_kernel(PeerPtrs params, int world, int rank, int64_t lo4, in
     if (j < nw) reinterpret_cast<float4*>(params.p[j])[i] = pp;
 }
 
+// ---- NVLS forms (mc = the segment's MULTICAST address, cuMulticast* mapping over all N ranks' segments): the NVSwitch
+// adds the N ranks' float4s in flight (multimem.ld_reduce) and replicates one store to all N buffers (multimem.st), so a
+// rank moves its 1/N slice once in each direction -- 4 B/param/N in and out instead of (N-1)/N * 4 B/param.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* mc_addr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+peer_reduce_scatter_mc_kernel(const float4* __restrict__ mc_grads, int64_t lo4, int64_t hi4, float4* __restrict__ gsum,
+                              double* __restrict__ partial) {
+  __shared__ float red[32];
+  float s = 0.f;
+  // a switch round trip per load: four independent multimem loads in flight per thread
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += 4 * stride) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < hi4) a[u] = multimem_ld_reduce_add(mc_grads + i + u * stride);   // sum over the N ranks, formed in the switch
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < hi4) {
+        gsum[i + u * stride - lo4] = a[u];
+        s = fmaf(a[u].x, a[u].x, s); s = fmaf(a[u].y, a[u].y, s); s = fmaf(a[u].z, a[u].z, s); s = fmaf(a[u].w, a[u].w, s);
+      }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
+}
+
+__global__ void __launch_bounds__(256)
+peer_adam_allgather_mc_kernel(const float4* __restrict__ my_params, float4* __restrict__ mc_params, int world, int64_t lo4,
+                              int64_t hi4, const float4* __restrict__ gsum, float4* __restrict__ m4, float4* __restrict__ v4,
+                              const double* __restrict__ norm2, int nphase, float* __restrict__ sq_out, float max_norm,
+                              float step_size, float b1, float b2, float inv_bc2_sqrt, float eps) {
+  double tot = 0.0;
+  for (int ph = 0; ph < nphase; ++ph)                       // fixed order: identical on every rank
+    for (int j = 0; j < world; ++j) tot += norm2[ph * kMaxRanks + j];
+  const float sq = (float)tot;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && sq_out) sq_out[0] = sq;
+  float coef = 1.f;
+  if (max_norm > 0.f) coef = fminf(1.0f, max_norm / (sqrtf(sq) + 1e-6f));
+  const int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi4) return;
+  const float4 gg = gsum[i - lo4];
+  float4 pp = my_params[i];
+  float4 mm = m4[i - lo4];
+  float4 vv = v4[i - lo4];
+  float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x = ga[e] * coef;
+    ma[e] = b1 * ma[e] + (1.f - b1) * x;
+    va[e] = b2 * va[e] + (1.f - b2) * x * x;
+    pa[e] -= step_size * ma[e] / (sqrtf(va[e]) * inv_bc2_sqrt + eps);
+  }
+  m4[i - lo4] = mm;
+  v4[i - lo4] = vv;
+  multimem_st(mc_params + i, pp);                           // one store, replicated by the switch into all N buffers
+}
+
 int fill(PeerPtrs* out, void* const* in, int world, size_t byte_off) {
   for (int j = 0; j < kMaxRanks; ++j)
     out->p[j] = (j < world) ? (void*)((char*)in[j] + byte_off) : nullptr;
@@ -218,8 +291,8 @@ extern "C" int64_t vmmt_peer_slice(int64_t n, int world, int rank, int64_t* lo, 
 // barrier -> reduce-scatter of the sub-range [begin, begin + n) of the flat gradient buffers (this rank's slice of
 // it) -> this rank's share of ||g||^2 published into norm slot array `phase` (0 or 1) of every peer.
 // Two phases let a step exchange a sub-range EARLY (beside the rest of the backward pass) and the remainder at the end.
-extern "C" int vmmt_peer_reduce_scatter(void* const* segments, size_t grad_off, int rank, int world, int64_t begin,
-                                        int64_t n, float* gsum, int phase, void* workspace, void* stream) {
+extern "C" int vmmt_peer_reduce_scatter(void* const* segments, void* mc_base, size_t grad_off, int rank, int world,
+                                        int64_t begin, int64_t n, float* gsum, int phase, void* workspace, void* stream) {
   VMMT_REQUIRE(segments && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
                "peer_reduce_scatter: bad rank/world");
   VMMT_REQUIRE(n > 0 && n % 4 == 0 && begin >= 0 && begin % 4 == 0, "peer_reduce_scatter: range must be 16-byte granular");
@@ -243,6 +316,13 @@ extern "C" int vmmt_peer_reduce_scatter(void* const* segments, size_t grad_off, 
   if (nblk > 2048) nblk = 2048;
   if (nblk < 1) nblk = 1;
   double* partial = (double*)workspace;
+  if (mc_base != nullptr && world > 1) {
+    peer_reduce_scatter_mc_kernel<<<nblk, 256, 0, s>>>(reinterpret_cast<const float4*>((const char*)mc_base + grad_off), lo4, hi4,
+                                                        (float4*)gsum, partial);
+    if ((rc = vmmt_check_launch("peer_reduce_scatter_mc"))) return rc;
+    peer_norm_publish_kernel<<<1, 256, 0, s>>>(partial, nblk, sig, rank, world, phase);
+    return vmmt_check_launch("peer_norm_publish");
+  }
   switch (world) {
 #define RS_CASE(W)                                                                               \
   case W:                                                                                        \
@@ -261,8 +341,8 @@ extern "C" int vmmt_peer_reduce_scatter(void* const* segments, size_t grad_off, 
 // [barrier ->] clip (total norm = sum over `nphase` slot arrays) + Adam on this rank's slice of [begin, begin + n),
 // new parameters stored into all N parameter buffers [-> barrier].  The barrier before is needed once after the last
 // reduce-scatter of a step, the barrier after once after the last update.
-extern "C" int vmmt_peer_adam_allgather(void* const* segments, size_t param_off, int rank, int world, int64_t begin,
-                                        int64_t n, const float* gsum, float* exp_avg, float* exp_avg_sq,
+extern "C" int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, size_t param_off, int rank, int world,
+                                        int64_t begin, int64_t n, const float* gsum, float* exp_avg, float* exp_avg_sq,
                                         float* sqnorm_out, int nphase, float max_norm, float lr, float beta1, float beta2,
                                         float eps, int64_t step, int barrier_before, int barrier_after, void* stream) {
   VMMT_REQUIRE(segments && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
@@ -290,6 +370,12 @@ extern "C" int vmmt_peer_adam_allgather(void* const* segments, size_t param_off,
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   const double* norm2 = reinterpret_cast<const double*>((const char*)segments[rank] + kNormOff);
   const int ablk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256);
+  if (mc_base != nullptr && world > 1) {
+    peer_adam_allgather_mc_kernel<<<ablk, 256, 0, s>>>(
+        reinterpret_cast<const float4*>((const char*)segments[rank] + param_off),
+        reinterpret_cast<float4*>((char*)mc_base + param_off), world, lo4, hi4, (const float4*)gsum, (float4*)exp_avg,
+        (float4*)exp_avg_sq, norm2, nphase, sqnorm_out, max_norm, step_size, beta1, beta2, inv_bc2_sqrt, eps);
+  } else
   switch (world) {
 #define AD_CASE(W)                                                                                \
   case W:                                                                                         \
@@ -313,13 +399,13 @@ extern "C" int vmmt_peer_adam_allgather(void* const* segments, size_t param_off,
 }
 
 // The whole flat buffer in one go: barrier -> reduce-scatter + norm -> barrier -> clip + Adam + all-gather -> barrier.
-extern "C" int vmmt_peer_adam_step(void* const* segments, size_t param_off, size_t grad_off, int rank,
+extern "C" int vmmt_peer_adam_step(void* const* segments, void* mc_base, size_t param_off, size_t grad_off, int rank,
                                    int world, int64_t n, float* gsum, float* exp_avg,
                                    float* exp_avg_sq, float* sqnorm_out, float max_norm, float lr,
                                    float beta1, float beta2, float eps, int64_t step, void* workspace,
                                    void* stream) {
-  int rc = vmmt_peer_reduce_scatter(segments, grad_off, rank, world, 0, n, gsum, 0, workspace, stream);
+  int rc = vmmt_peer_reduce_scatter(segments, mc_base, grad_off, rank, world, 0, n, gsum, 0, workspace, stream);
   if (rc) return rc;
-  return vmmt_peer_adam_allgather(segments, param_off, rank, world, 0, n, gsum, exp_avg, exp_avg_sq, sqnorm_out, 1,
+  return vmmt_peer_adam_allgather(segments, mc_base, param_off, rank, world, 0, n, gsum, exp_avg, exp_avg_sq, sqnorm_out, 1,
                                   max_norm, lr, beta1, beta2, eps, step, 1, 1, stream);
 }

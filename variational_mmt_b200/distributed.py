@@ -137,6 +137,40 @@ class PeerExchange(object):
         self.base = None
         self.flat = self.gflat = None
         self._opened = []
+        self.mc_base = None            # multicast address of the segments (NVLS: multimem.ld_reduce / multimem.st), or None
+        self._symm = None              # (tensor, handle) of torch's symmetric memory when the segment lives there
+
+    @classmethod
+    def _create_symmetric(cls, self, nbytes, device):
+        """The segment in torch's symmetric memory (cuMem allocation + peer mappings + one cuMulticast object over all
+        ranks' segments): gives the NVLS multicast address.  torch.distributed is plumbing here; every kernel that touches
+        the memory is ours (csrc/peer.cu).  Returns False (on every rank alike) when unavailable."""
+        ok = True
+        try:
+            import torch.distributed._symmetric_memory as sm
+            t = sm.empty(nbytes // 4, dtype=torch.float32, device=device)
+            t.zero_()
+            torch.cuda.synchronize(device)
+            h = sm.rendezvous(t, dist.group.WORLD)
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            mc = int(h.multicast_ptr)
+            ok = len(ptrs) == self.world and mc != 0
+        except Exception as e:                                # noqa: BLE001
+            ok, t, h, ptrs, mc = False, None, None, None, 0
+            if self.rank == 0:
+                sys.stderr.write("variational_mmt_b200: symmetric memory unavailable (%s)\n" % e)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, ok)
+        if not all(oks):
+            return False
+        self._symm = (t, h)
+        self.base = ptrs[self.rank]
+        self.mc_base = mc
+        self.segments = (ctypes.c_void_p * self.world)(*ptrs)
+        self.flat = t[self.param_off // 4: self.param_off // 4 + self.n]
+        self.gflat = t[self.grad_off // 4: self.grad_off // 4 + self.n]
+        self.device = device
+        return True
 
     @classmethod
     def create(cls, n_floats, device):
@@ -147,6 +181,15 @@ class PeerExchange(object):
         self.param_off = sig
         self.grad_off = sig + ((self.n * 4 + 255) // 256) * 256
         nbytes = self.grad_off + ((self.n * 4 + 255) // 256) * 256
+        # NVLS (multimem through the switch) or P2P loads / stores?  Measured on 8 x B200 (tools/dp_step_prof.py, one-phase
+        # step over 42.8 M parameters): N=2 611 vs 338 us, N=4 540 vs 450 us, N=8 549 vs 587 us -- the reduce-scatter's
+        # contributions still leave every GPU at (N-1)/N * 4 B/param and the all-gather still arrives at that rate, the
+        # switch only thins the opposite direction, and one multimem access costs more than a peer access.  Default: NVLS
+        # from 8 ranks on; VMMT_DP_NVLS=1 / 0 forces it on / off.
+        want = os.environ.get("VMMT_DP_NVLS")
+        use_nvls = (want == "1") if want in ("0", "1") else self.world >= 8
+        if self.world > 1 and use_nvls and cls._create_symmetric(self, nbytes, device):
+            return self
         hb = int(L.lib.vmmt_peer_handle_bytes())
         handle = ctypes.create_string_buffer(hb)
         base = ctypes.c_void_p()
