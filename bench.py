@@ -274,6 +274,7 @@ def run_ours(args):
             else:
                 step(resident[i % NB], False)
             tok += tokens[i % NB]
+        optim.wait_params()                               # the last update's overlapped all-gather belongs to the timed region
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0

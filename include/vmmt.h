@@ -222,6 +222,10 @@ int vmmt_generator_topk_supported(const float* x, const float* W, int M, int H, 
 int vmmt_generator_topk(const float* x, const float* W, const float* b, int M, int H, int V, int K, void* workspace,
                         size_t workspace_bytes, int flags, void* stream);
 
+/* up to 5 device-to-device copies in one launch (a captured step's static input buffers; TrainerMultimodal.py:632-677 builds
+ * the batch tensors per step): SM threads instead of a copy engine. */
+int vmmt_copy_list(const void* const* src, void* const* dst, const int64_t* bytes, int n, void* stream);
+
 /* ---- optimiser: global-norm clip + Adam on flat buffers (Optim.py:69-70,94-96) */
 /* model.zero_grad() (TrainerMultimodal.py:627-628) on the flat gradient buffer with at most max_blocks resident blocks
  * (0 = one per SM), so that it can run beside latency-critical kernels without starving them of SM slots or HBM. */
@@ -244,8 +248,10 @@ int vmmt_peer_alloc(size_t bytes, void** ptr, void* handle_out /* vmmt_peer_hand
 int vmmt_peer_open(const void* handle, void** ptr);
 int vmmt_peer_close(void* ptr);
 int vmmt_peer_free(void* ptr);
-/* cross-GPU barrier kernel on `stream` (flag words in the signal blocks, device-resident generation counter). */
-int vmmt_peer_barrier(void* const* segments, int rank, int world, void* stream);
+/* cross-GPU barrier kernel on `stream` (flag words in the signal blocks, device-resident generation counter).  Two
+ * independent barrier CHANNELS (0, 1): barriers issued from two streams that may run concurrently (the all-gather of the
+ * buffer's tail overlapped with the next step) must use different channels. */
+int vmmt_peer_barrier(void* const* segments, int rank, int world, int channel, void* stream);
 size_t vmmt_peer_adam_workspace_bytes(void);
 /* [*lo, *hi) = the floats of an n-float flat buffer rank `rank` reduces and updates; returns the slice capacity
  * (floats) every rank allocates for gsum / exp_avg / exp_avg_sq. */
@@ -262,7 +268,7 @@ int vmmt_peer_reduce_scatter(void* const* segments, void* mc_base, size_t grad_o
 int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, size_t param_off, int rank, int world, int64_t begin,
                              int64_t n, const float* gsum, float* exp_avg, float* exp_avg_sq, float* sqnorm_out, int nphase,
                              float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
-                             int barrier_before, int barrier_after, void* stream);
+                             int barrier_before, int barrier_after, int channel, void* stream);
 /* barrier -> reduce-scatter (P2P loads, rank-ordered sum) + ||g||^2 share -> barrier -> clip + Adam on the slice,
  * new parameters stored into all N parameter buffers (P2P stores) -> barrier.  sqnorm_out (optional) receives the
  * squared global norm of the summed gradient.  No NCCL, no host synchronisation, CUDA-graph capturable. */

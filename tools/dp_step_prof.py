@@ -46,7 +46,7 @@ for it in range(10):
     _lib.set_profile(prof)
     _lib.call("vmmt_peer_reduce_scatter", pe.segments, pe.mc_base, pe.grad_off, pe.rank, pe.world, 0, n, fptr(o._gsum), 0, fptr(o._pws), stream())
     _lib.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, 0, n, fptr(o._gsum), fptr(o.exp_avg),
-              fptr(o.exp_avg_sq), fptr(o._sq), 1, 5.0, 0.002, 0.9, 0.999, 1e-9, 20 + it, 1, 1, stream())
+              fptr(o.exp_avg_sq), fptr(o._sq), 1, 5.0, 0.002, 0.9, 0.999, 1e-9, 20 + it, 1, 1, 0, stream())
     torch.cuda.synchronize()
     _lib.set_profile(None)
     for nme, a, a0, a1 in prof:

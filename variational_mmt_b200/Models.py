@@ -172,6 +172,12 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             ops.arm_early_exchange(hook)
         if self.conditional:
             ops.join_branch(tgt_context)
+        ready = getattr(self, "params_ready_hook", None)
+        if ready is not None:
+            # data parallel (Optim.enable_early_exchange): the previous update's all-gather of the buffer's tail -- the
+            # latent / image networks and the generator, first read below -- runs under this step's encoder phase; wait
+            # for it here (an external-event wait node when the step is a captured graph)
+            ready()
         if self.training and dec_state is None and hasattr(self.decoder, "input_projection"):
             # decoder input projection emb(tgt) W_ih[:, :E]^T: needs neither the encoders nor z.  It is issued HERE, beside
             # the latent networks (batch-row MLPs that leave most SMs idle), and not beside the encoder recurrences: a

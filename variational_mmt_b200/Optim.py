@@ -110,6 +110,7 @@ class Optim(object):
     def _adam_state_dict(self):
         if getattr(self, "flat", None) is None:
             return self._pending_state
+        self.wait_params()
         n = self.flat.numel()
         m = torch.zeros(n, device=self.flat.device, dtype=torch.float32)
         v = torch.zeros_like(m)
@@ -220,6 +221,16 @@ class Optim(object):
                        "stream": torch.cuda.Stream(device=dev, priority=-1)}
         self.exp_avg = self.exp_avg_sq = self._gsum = None       # replaced by the per-range slices above
         model.early_exchange_hook = self.early_reduce_scatter
+        if os.environ.get("VMMT_DP_AG_OVERLAP", "0") == "1":
+            # overlapped all-gather of the tail range: an EXTERNAL event (recorded by step() outside any captured graph,
+            # waited for inside the captured forward pass) marks "the tail parameters of the previous update have landed".
+            # OFF by default: measured on 2 / 8 B200s (tools/dp_ab.sh, profiles/dp_exchange_r2.txt) it hides the ~130 us tail
+            # all-gather but the arriving NVLink traffic holds up the first copies / kernels of the next step by as much
+            # (2.166 vs 2.162 ms at 8 GPUs): no net gain, so the simpler in-order schedule stays the default
+            ag = {"stream": torch.cuda.Stream(device=dev, priority=-1), "event": torch.cuda.Event(external=True)}
+            ag["event"].record(torch.cuda.current_stream(dev))      # created before any capture waits for it
+            self._early["ag"] = ag
+            model.params_ready_hook = self.wait_params
         if carried is not None:
             self._load_adam_state(carried)
         torch.cuda.synchronize(dev)
@@ -249,6 +260,14 @@ class Optim(object):
                    fptr(e["gsum_a"]), 1, fptr(e["ws_a"]), stream())
         self._early_done = True
 
+    def wait_params(self):
+        """The current stream waits until the overlapped all-gather of the previous update has delivered every parameter
+        (no-op without it).  NMTVIModel.forward calls this before the latent networks; call it yourself before reading the
+        parameters from another stream / the host (evaluation, checkpointing) between steps."""
+        ag = (self._early or {}).get("ag")
+        if ag is not None:
+            torch.cuda.current_stream(self.flat.device).wait_event(ag["event"])
+
     def join_early(self):
         """The current stream waits for the early reduce-scatter (a captured step must join it before the capture ends)."""
         if self._early is not None and self._early_done:
@@ -260,8 +279,9 @@ class Optim(object):
             if (self.peer is not None and self.peer.mc_base) else "nvlink p2p reduce-scatter + sharded clip/Adam + all-gather"
         if self.peer is not None and self._early is not None:
             return (how + " (csrc/peer.cu); tail of the buffer (latent / image networks, generator: %.0f%%) "
-                    "reduce-scattered beside the encoder backward"
-                    % (100.0 * (self.flat.numel() - self._early["begin"]) / self.flat.numel()))
+                    "reduce-scattered beside the encoder backward%s"
+                    % (100.0 * (self.flat.numel() - self._early["begin"]) / self.flat.numel(),
+                       " and all-gathered under the next step's encoder phase" if self._early.get("ag") else ""))
         if self.peer is not None:
             return how + " (csrc/peer.cu)"
         return "nccl all-reduce + replicated clip/Adam" if distributed.is_active() else "single rank"
@@ -300,10 +320,25 @@ class Optim(object):
             hyp = (max_norm, float(self.lr), float(self.betas[0]), float(self.betas[1]), 1e-9, self._adam_t)
             L.call("vmmt_peer_reduce_scatter", pe.segments, pe.mc_base, pe.grad_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]), 0,
                    fptr(self._pws), sm)
-            L.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, b0, n - b0, fptr(e["gsum_a"]),
-                   fptr(e["m_a"]), fptr(e["v_a"]), fptr(self._sq), 2, *hyp, 1, 0, sm)
+            # head of the buffer first (embeddings, encoders, decoder: what the next forward pass reads first), bracketed by
+            # barriers: norm shares landed / nobody reads my gradients any more -> update + all-gather -> every rank's head
+            # parameters are complete
             L.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, 0, b0, fptr(e["gsum_b"]),
-                   fptr(e["m_b"]), fptr(e["v_b"]), None, 2, *hyp, 0, 1, sm)
+                   fptr(e["m_b"]), fptr(e["v_b"]), fptr(self._sq), 2, *hyp, 1, 1, 0, sm)
+            # the tail (latent / image networks, generator: first read ~250 us into the next forward pass) is updated and
+            # all-gathered on its own stream with its own barrier channel, UNDER the next step's encoder phase; the model
+            # waits for `ag["event"]` (NMTVIModel.params_ready_hook) before it touches those parameters
+            ag = e.get("ag")
+            cur = torch.cuda.current_stream(self.flat.device)
+            if ag is not None:
+                ag["stream"].wait_stream(cur)
+                with torch.cuda.stream(ag["stream"]):
+                    L.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, b0, n - b0,
+                           fptr(e["gsum_a"]), fptr(e["m_a"]), fptr(e["v_a"]), None, 2, *hyp, 0, 1, 1, stream())
+                    ag["event"].record(ag["stream"])
+            else:
+                L.call("vmmt_peer_adam_allgather", pe.segments, pe.mc_base, pe.param_off, pe.rank, pe.world, b0, n - b0,
+                       fptr(e["gsum_a"]), fptr(e["m_a"]), fptr(e["v_a"]), None, 2, *hyp, 0, 1, 0, sm)
             return
         if self.peer is not None:
             pe = self.peer

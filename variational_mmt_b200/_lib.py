@@ -88,6 +88,7 @@ SIGNATURES = {
     "vmmt_generator_topk_supported": (I, [P, P, I, I, I, I]),
     "vmmt_generator_topk": (I, [P, P, P, I, I, I, I, P, SZ, I, P]),
     "vmmt_fill_zero": (I, [P, L, I, P]),
+    "vmmt_copy_list": (I, [P, P, P, I, P]),
     "vmmt_sqnorm_workspace_bytes": (SZ, []),
     "vmmt_sqnorm": (I, [P, L, P, I, P, P]),
     "vmmt_adam_clip_step": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),
@@ -97,11 +98,11 @@ SIGNATURES = {
     "vmmt_peer_open": (I, [P, C.POINTER(P)]),
     "vmmt_peer_close": (I, [P]),
     "vmmt_peer_free": (I, [P]),
-    "vmmt_peer_barrier": (I, [P, I, I, P]),
+    "vmmt_peer_barrier": (I, [P, I, I, I, P]),
     "vmmt_peer_adam_workspace_bytes": (SZ, []),
     "vmmt_peer_slice": (L, [L, I, I, C.POINTER(L), C.POINTER(L)]),
     "vmmt_peer_reduce_scatter": (I, [P, P, SZ, I, I, L, L, P, I, P, P]),
-    "vmmt_peer_adam_allgather": (I, [P, P, SZ, I, I, L, L, P, P, P, P, I, F, F, F, F, F, L, I, I, P]),
+    "vmmt_peer_adam_allgather": (I, [P, P, SZ, I, I, L, L, P, P, P, P, I, F, F, F, F, F, L, I, I, I, P]),
     "vmmt_peer_adam_step": (I, [P, P, SZ, SZ, I, I, L, P, P, P, P, F, F, F, F, F, L, P, P]),
     "vmmt_beam_advance": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),
     "vmmt_beam_advance_topk": (I, [P, I, I, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, P]),

@@ -105,6 +105,39 @@ extern "C" int vmmt_fill_zero(float* p, int64_t n, int max_blocks, void* stream)
   return vmmt_check_launch("fill_zero");
 }
 
+namespace {
+// up to 5 small device-to-device copies in ONE launch (the step's static input buffers): done by SM threads, not by a copy
+// engine -- measured: a cudaMemcpyAsync issued while the previous update's all-gather was still arriving over NVLink sat
+// for 125 us (8 GPUs) before it completed, a kernel launched beside the same traffic is not held up
+struct CopyList { const char* src[5]; char* dst[5]; long long bytes[5]; int n; };
+__global__ void copy_list_kernel(const CopyList L) {
+  for (int j = 0; j < L.n; ++j) {
+    const long long nb = L.bytes[j];
+    const bool vec = ((reinterpret_cast<uintptr_t>(L.src[j]) | reinterpret_cast<uintptr_t>(L.dst[j])) & 15) == 0;
+    const long long n16 = vec ? nb / 16 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+      reinterpret_cast<uint4*>(L.dst[j])[i] = reinterpret_cast<const uint4*>(L.src[j])[i];
+    for (long long i = n16 * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x)
+      L.dst[j][i] = L.src[j][i];
+  }
+}
+}  // namespace
+
+extern "C" int vmmt_copy_list(const void* const* src, void* const* dst, const int64_t* bytes, int n, void* stream) {
+  VMMT_REQUIRE(n >= 1 && n <= 5 && src && dst && bytes, "copy_list: 1..5 copies");
+  CopyList L;
+  long long mx = 0;
+  for (int j = 0; j < n; ++j) {
+    L.src[j] = (const char*)src[j]; L.dst[j] = (char*)dst[j]; L.bytes[j] = bytes[j];
+    if (bytes[j] > mx) mx = bytes[j];
+  }
+  L.n = n;
+  int nblk = ceil_div(mx / 16 + 1, 256);
+  if (nblk > 64) nblk = 64;
+  copy_list_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(L);
+  return vmmt_check_launch("copy_list");
+}
+
 extern "C" size_t vmmt_sqnorm_workspace_bytes(void) { return 1024 * sizeof(double); }
 
 extern "C" int vmmt_sqnorm(const float* g, int64_t n, float* out, int accumulate, void* workspace,

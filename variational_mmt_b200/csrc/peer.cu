@@ -38,6 +38,9 @@ constexpr int kMaxRanks = 16;
 //   [64,  68)   epoch              u32, local barrier generation
 //   [128, 256)  norm2[0][kMaxRanks]  f64, slot j written by rank j (its share of ||g||^2 of exchange phase 0)
 //   [256, 384)  norm2[1][kMaxRanks]  same for phase 1 (the early, overlapped reduce-scatter of a sub-range)
+//   [384, 448)  arrive[kMaxRanks] of barrier CHANNEL 1, [448, 452) its epoch: barriers issued from a second stream
+//               (the all-gather of the buffer's tail, overlapped with the next step's forward pass) must not share
+//               the generation counter of the main stream's barriers
 constexpr int kSigBytes = 512;
 constexpr int kNormOff = 128;
 
@@ -55,17 +58,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
 }
 
 // One block.  Thread j < world signals rank j and waits for rank j.
-__global__ void peer_barrier_kernel(PeerPtrs sig, int rank, int world) {
+__global__ void peer_barrier_kernel(PeerPtrs sig, int rank, int world, int channel) {
+  const int aw = channel ? 96 : 0, ew = channel ? 112 : 16;       // word offsets of the channel's arrive[] / epoch
   uint32_t* mine = reinterpret_cast<uint32_t*>(sig.p[rank]);
-  const uint32_t e = mine[16] + 1;                       // epoch
+  const uint32_t e = mine[ew] + 1;                       // epoch
   __syncthreads();
-  if (threadIdx.x == 0) mine[16] = e;
+  if (threadIdx.x == 0) mine[ew] = e;
   const int j = threadIdx.x;
   if (j < world) {
     __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t*>(sig.p[j]) + rank, e);
+    st_release_sys(reinterpret_cast<uint32_t*>(sig.p[j]) + aw + rank, e);
     // a peer is at most one generation ahead of me, so ">= e" (wrap-safe) is the arrival test
-    while ((int32_t)(ld_acquire_sys(mine + j) - e) < 0) __nanosleep(40);
+    while ((int32_t)(ld_acquire_sys(mine + aw + j) - e) < 0) __nanosleep(40);
   }
   __syncthreads();
 }
@@ -132,25 +136,25 @@ peer_adam_allgather_kernel(PeerPtrs params, int world, int rank, int64_t lo4, in
   if (blockIdx.x == 0 && threadIdx.x == 0 && sq_out) sq_out[0] = sq;
   float coef = 1.f;
   if (max_norm > 0.f) coef = fminf(1.0f, max_norm / (sqrtf(sq) + 1e-6f));
-  const int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hi4) return;
-  const float4 gg = gsum[i - lo4];
-  float4 pp = reinterpret_cast<const float4*>(params.p[rank])[i];
-  float4 mm = m4[i - lo4];
-  float4 vv = v4[i - lo4];
-  float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+  for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gg = gsum[i - lo4];
+    float4 pp = reinterpret_cast<const float4*>(params.p[rank])[i];
+    float4 mm = m4[i - lo4];
+    float4 vv = v4[i - lo4];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float x = ga[e] * coef;
-    ma[e] = b1 * ma[e] + (1.f - b1) * x;
-    va[e] = b2 * va[e] + (1.f - b2) * x * x;
-    pa[e] -= step_size * ma[e] / (sqrtf(va[e]) * inv_bc2_sqrt + eps);
+    for (int e = 0; e < 4; ++e) {
+      const float x = ga[e] * coef;
+      ma[e] = b1 * ma[e] + (1.f - b1) * x;
+      va[e] = b2 * va[e] + (1.f - b2) * x * x;
+      pa[e] -= step_size * ma[e] / (sqrtf(va[e]) * inv_bc2_sqrt + eps);
+    }
+    m4[i - lo4] = mm;
+    v4[i - lo4] = vv;
+#pragma unroll
+    for (int j = 0; j < ((W > 0) ? W : kMaxRanks); ++j)
+      if (j < nw) reinterpret_cast<float4*>(params.p[j])[i] = pp;
   }
-  m4[i - lo4] = mm;
-  v4[i - lo4] = vv;
-#pragma unroll
-  for (int j = 0; j < ((W > 0) ? W : kMaxRanks); ++j)
-    if (j < nw) reinterpret_cast<float4*>(params.p[j])[i] = pp;
 }
 
 // ---- NVLS forms (mc = the segment's MULTICAST address, cuMulticast* mapping over all N ranks' segments): the NVSwitch
@@ -202,23 +206,23 @@ peer_adam_allgather_mc_kernel(const float4* __restrict__ my_params, float4* __re
   if (blockIdx.x == 0 && threadIdx.x == 0 && sq_out) sq_out[0] = sq;
   float coef = 1.f;
   if (max_norm > 0.f) coef = fminf(1.0f, max_norm / (sqrtf(sq) + 1e-6f));
-  const int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hi4) return;
-  const float4 gg = gsum[i - lo4];
-  float4 pp = my_params[i];
-  float4 mm = m4[i - lo4];
-  float4 vv = v4[i - lo4];
-  float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+  for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gg = gsum[i - lo4];
+    float4 pp = my_params[i];
+    float4 mm = m4[i - lo4];
+    float4 vv = v4[i - lo4];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float x = ga[e] * coef;
-    ma[e] = b1 * ma[e] + (1.f - b1) * x;
-    va[e] = b2 * va[e] + (1.f - b2) * x * x;
-    pa[e] -= step_size * ma[e] / (sqrtf(va[e]) * inv_bc2_sqrt + eps);
+    for (int e = 0; e < 4; ++e) {
+      const float x = ga[e] * coef;
+      ma[e] = b1 * ma[e] + (1.f - b1) * x;
+      va[e] = b2 * va[e] + (1.f - b2) * x * x;
+      pa[e] -= step_size * ma[e] / (sqrtf(va[e]) * inv_bc2_sqrt + eps);
+    }
+    m4[i - lo4] = mm;
+    v4[i - lo4] = vv;
+    multimem_st(mc_params + i, pp);                         // one store, replicated by the switch into all N buffers
   }
-  m4[i - lo4] = mm;
-  v4[i - lo4] = vv;
-  multimem_st(mc_params + i, pp);                           // one store, replicated by the switch into all N buffers
 }
 
 int fill(PeerPtrs* out, void* const* in, int world, size_t byte_off) {
@@ -261,12 +265,13 @@ extern "C" int vmmt_peer_free(void* ptr) {
   return VMMT_OK;
 }
 
-extern "C" int vmmt_peer_barrier(void* const* segments, int rank, int world, void* stream) {
+extern "C" int vmmt_peer_barrier(void* const* segments, int rank, int world, int channel, void* stream) {
   VMMT_REQUIRE(segments && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
                "peer_barrier: bad rank/world");
+  VMMT_REQUIRE(channel == 0 || channel == 1, "peer_barrier: channel must be 0 or 1");
   PeerPtrs sig;
   fill(&sig, segments, world, 0);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sig, rank, world);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sig, rank, world, channel);
   return vmmt_check_launch("peer_barrier");
 }
 
@@ -306,7 +311,7 @@ extern "C" int vmmt_peer_reduce_scatter(void* const* segments, void* mc_base, si
   range_slice(begin, n, world, rank, &lo, &hi);
   const int64_t lo4 = lo / 4, hi4 = hi / 4, cnt4 = hi4 - lo4;
   int rc;
-  peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
+  peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world, 0);
   if ((rc = vmmt_check_launch("peer_barrier"))) return rc;
   int nblk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256 * 2);
   // phase 1 runs BESIDE the encoders' backward recurrences: two light blocks per SM leave room for their thread-block
@@ -344,12 +349,14 @@ extern "C" int vmmt_peer_reduce_scatter(void* const* segments, void* mc_base, si
 extern "C" int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, size_t param_off, int rank, int world,
                                         int64_t begin, int64_t n, const float* gsum, float* exp_avg, float* exp_avg_sq,
                                         float* sqnorm_out, int nphase, float max_norm, float lr, float beta1, float beta2,
-                                        float eps, int64_t step, int barrier_before, int barrier_after, void* stream) {
+                                        float eps, int64_t step, int barrier_before, int barrier_after, int channel,
+                                        void* stream) {
   VMMT_REQUIRE(segments && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
                "peer_adam_allgather: bad rank/world");
   VMMT_REQUIRE(n > 0 && n % 4 == 0 && begin >= 0 && begin % 4 == 0, "peer_adam_allgather: range must be 16-byte granular");
   VMMT_REQUIRE(param_off % 16 == 0, "peer_adam_allgather: offsets must be 16-byte aligned");
   VMMT_REQUIRE(step >= 1 && (nphase == 1 || nphase == 2), "peer_adam_allgather: bad step / nphase");
+  VMMT_REQUIRE(channel == 0 || channel == 1, "peer_adam_allgather: channel must be 0 or 1");
   VMMT_REQUIRE((((uintptr_t)gsum | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
                "peer_adam_allgather: slice buffers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
@@ -361,7 +368,7 @@ extern "C" int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, si
   const int64_t lo4 = lo / 4, hi4 = hi / 4, cnt4 = hi4 - lo4;
   int rc;
   if (barrier_before) {
-    peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world, channel);
     if ((rc = vmmt_check_launch("peer_barrier"))) return rc;
   }
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
@@ -369,7 +376,11 @@ extern "C" int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, si
   const float step_size = (float)((double)lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   const double* norm2 = reinterpret_cast<const double*>((const char*)segments[rank] + kNormOff);
-  const int ablk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256);
+  // channel 1 = the overlapped all-gather of the tail: it runs BESIDE the next step's encoder recurrences, whose
+  // thread-block clusters need whole GPC slices free at once -- one light block per SM (no shared / tensor memory: it
+  // co-resides with a recurrence or GEMM CTA) instead of a grid that floods the block scheduler
+  int ablk = ceil_div(cnt4 > 0 ? cnt4 : 1, 256);
+  if (channel == 1) ablk = min(ablk, vmmt_num_sms());
   if (mc_base != nullptr && world > 1) {
     peer_adam_allgather_mc_kernel<<<ablk, 256, 0, s>>>(
         reinterpret_cast<const float4*>((const char*)segments[rank] + param_off),
@@ -392,7 +403,7 @@ extern "C" int vmmt_peer_adam_allgather(void* const* segments, void* mc_base, si
   }
   if ((rc = vmmt_check_launch("peer_adam_allgather"))) return rc;
   if (barrier_after) {
-    peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(sig, rank, world, channel);
     return vmmt_check_launch("peer_barrier");
   }
   return VMMT_OK;
@@ -407,5 +418,5 @@ extern "C" int vmmt_peer_adam_step(void* const* segments, void* mc_base, size_t 
   int rc = vmmt_peer_reduce_scatter(segments, mc_base, grad_off, rank, world, 0, n, gsum, 0, workspace, stream);
   if (rc) return rc;
   return vmmt_peer_adam_allgather(segments, mc_base, param_off, rank, world, 0, n, gsum, exp_avg, exp_avg_sq, sqnorm_out, 1,
-                                  max_norm, lr, beta1, beta2, eps, step, 1, 1, stream);
+                                  max_norm, lr, beta1, beta2, eps, step, 1, 1, 0, stream);
 }

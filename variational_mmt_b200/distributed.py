@@ -245,7 +245,7 @@ class PeerExchange(object):
     def barrier(self):
         """Device-side barrier over the peer segments on the current stream (no host synchronisation)."""
         from . import _lib as L
-        L.call("vmmt_peer_barrier", self.segments, self.rank, self.world, L.stream())
+        L.call("vmmt_peer_barrier", self.segments, self.rank, self.world, 0, L.stream())
 
     def close(self):
         from . import _lib as L

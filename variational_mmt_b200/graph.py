@@ -76,6 +76,20 @@ class GraphedTrainStep(object):
             self.optim.join_early()      # the early reduce-scatter forked inside the backward pass rejoins the step here
         return st._vec
 
+    def _load_inputs(self, static, inputs):
+        """Copies this step's batch into the graph's static buffers: one kernel launch for device-resident inputs (no copy
+        engine: see vmmt_copy_list), cudaMemcpyAsync for host (pinned) inputs."""
+        if all(t.is_cuda and t.is_contiguous() and t.dtype == s.dtype for s, t in zip(static, inputs)) and len(inputs) <= 5:
+            import ctypes as C
+            n = len(inputs)
+            src = (C.c_void_p * n)(*[t.data_ptr() for t in inputs])
+            dst = (C.c_void_p * n)(*[s.data_ptr() for s in static])
+            nb = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in inputs])
+            _lib.call("vmmt_copy_list", src, dst, nb, n, _lib.stream())
+            return
+        for s, t in zip(static, inputs):
+            s.copy_(t, non_blocking=True)
+
     def _capture(self, key, inputs, normalization):
         if len(self._graphs) >= self.max_graphs:
             raise RuntimeError("GraphedTrainStep: too many shape buckets; bucket the batches by length")
@@ -134,8 +148,7 @@ class GraphedTrainStep(object):
         if gen != self._param_addresses():
             raise RuntimeError("GraphedTrainStep: the parameters were moved to other buffers after this graph was captured "
                                "(Optim.set_parameters / model.to()): create the GraphedTrainStep after Optim.set_parameters")
-        for s, t in zip(static, inputs):
-            s.copy_(t, non_blocking=True)
+        self._load_inputs(static, inputs)
         g.replay()
         if self.optim is not None and getattr(self.optim, "_early", None) is not None:
             self.optim._early_done = True          # the graph contains Optim.early_reduce_scatter (fired in its backward)
