@@ -332,8 +332,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
   const int Kp = P.Kp, nkb = Kp / 64;
   const uint32_t tile_bytes = (uint32_t)(Kp / 8) * CHUNK;    // one h operand tile [Kp/8 chunks][NRG][8 rows][8 fp16]
   uint8_t* Bt = sm;                                          // [2][tile]
-  float* gsm = reinterpret_cast<float*>(Bt + 2 * tile_bytes);                 // [4 gates][NPc][32]
-  uint8_t* hstage = reinterpret_cast<uint8_t*>(gsm + 4 * NPc * 32);           // [2][SLICE]
+  // gate exchange, double buffered by step parity: the reads of step s and the writes of step s+1 are ordered only through
+  // the mbarrier chain (h hand-off -> MMA -> accumulator), the writes of step s+2 also by two named barriers
+  float* gsm0 = reinterpret_cast<float*>(Bt + 2 * tile_bytes);                // [2][4 gates][NPc][32]
+  uint8_t* hstage = reinterpret_cast<uint8_t*>(gsm0 + 2 * 4 * NPc * 32);      // (unused tail kept for alignment of the barriers)
   uint64_t* bars = reinterpret_cast<uint64_t*>(hstage + 2 * SLICE);           // [0] mma_done, [1..2] h_full[buf]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* wstage = reinterpret_cast<float*>(bars + 4);                         // [EW][32][WST] weight-load staging
@@ -490,6 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_fwd_kernel(const TcFwdPara
       mbar_wait(bar_mma, (uint32_t)(s & 1));
       if (tr && tid == 0) P.trace[3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* gsm = gsm0 + (size_t)buf * 4 * NPc * 32;
       {
         // gate q of batch columns [hf HN, hf HN + HN): the four chains' partial sums
         uint32_t v[4][HN];
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
     if (warp == EW) {
       if (stop) break;
       if (leader) {
-        mbar_arrive_expect_tx(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)C * part_bytes);
+        mbar_arrive_expect_tx(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)(C - 1) * part_bytes);   // the C - 1 PEERS' blocks
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int mt = 0; mt < (P.floor ? 1 : n_mt); ++mt) {
 #pragma unroll
@@ -810,8 +813,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       // reduce-scatter: one block of nn rows per owner, into the owner's recv[buf][src = this CTA], completing on
       // the owner's recv_full[buf].  stage[buf] / recv[buf] are reused at step s+2: by then this CTA has consumed
       // every owner's step-(s+1) block, each sent after that owner consumed this step's copies.
+      // (the block this CTA owns itself is read straight from `stage` below: a bulk copy targets ANOTHER CTA)
       const int dstc = (lane < 2) ? warp * 2 + lane : 99;
-      if (dstc < C) {
+      if (dstc < C && dstc != crank) {
         const uint32_t dst = mapa(recv_addr + (uint32_t)((buf * 16 + crank) * PART), (uint32_t)dstc);
         const uint32_t bar = mapa(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)dstc);
         bulk_copy_to_cluster(dst, stage_addr + (uint32_t)((buf * 16 + dstc) * PART), part_bytes, bar);
@@ -821,18 +825,22 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       mbar_wait(bar_recv0 + 8u * (uint32_t)buf, (uint32_t)((s >> 1) & 1));
       if (tr && tid == 0) P.trace[4] = clock64();
       const float* rb = recv + (size_t)buf * 16 * NPc * 32;
+      const float* own = st + (size_t)crank * NPc * 32;      // this CTA's own partial block never left shared memory
+      auto part = [&](int src, int n) -> float {
+        return src == crank ? own[n * 32 + lane] : rb[(src * NPc + n) * 32 + lane];
+      };
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         if (r < nr) {
           const int n = warp + 8 * r;
           float s0 = dhr[r], s1 = 0.f, s2 = 0.f, s3 = 0.f;  // dhr: non-zero only for frozen (masked) cells
           for (int src = 0; src + 3 < C; src += 4) {
-            s0 += rb[((src + 0) * NPc + n) * 32 + lane];
-            s1 += rb[((src + 1) * NPc + n) * 32 + lane];
-            s2 += rb[((src + 2) * NPc + n) * 32 + lane];
-            s3 += rb[((src + 3) * NPc + n) * 32 + lane];
+            s0 += part(src + 0, n);
+            s1 += part(src + 1, n);
+            s2 += part(src + 2, n);
+            s3 += part(src + 3, n);
           }
-          for (int src = C & ~3; src < C; ++src) s0 += rb[(src * NPc + n) * 32 + lane];
+          for (int src = C & ~3; src < C; ++src) s0 += part(src, n);
           dhr[r] = (s0 + s1) + (s2 + s3);
         }
       }
@@ -859,7 +867,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
 struct TcPlan { int C, G, Ng, Kp, nrg; };
 
 size_t fwd_smem(int Kp, int nrg) {
-  return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64 +
+  return 128 + (size_t)2 * (Kp / 8) * nrg * 128 + (size_t)2 * 4 * 8 * nrg * 32 * 4 + (size_t)2 * 4 * nrg * 128 + 64 +
          (size_t)EW * 32 * WST * 4;
 }
 size_t bwd_smem(int nrg) { return 1024 + (size_t)2 * 2 * 8 * nrg * 128 + (size_t)4 * 16 * 8 * nrg * 32 * 4 + 64; }
