@@ -122,7 +122,8 @@ class GraphedTrainStep(object):
         # captured on a HIGH-priority stream (as are the branch / loss streams): kernel-node priorities are recorded, so
         # the critical chain's CTAs are placed before those of the weight-gradient lanes (default = lowest priority)
         if self._capture_stream is None:
-            self._capture_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            import os
+            self._capture_stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("VMMT_MAIN_PRIO", "-1")))
         with torch.cuda.graph(g, pool=self._pool, stream=self._capture_stream):
             ops.begin_step()
             vec = self._run(*static, normalization)

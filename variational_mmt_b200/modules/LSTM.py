@@ -55,10 +55,11 @@ class LSTM(nn.Module):
             c0 = hx[1][l * ndir:(l + 1) * ndir] if hx is not None else None
             cfg = {"save": save, "in_cols": in_cols if l == 0 else None, "gx_given": gx_given and l == 0,
                    "cluster_budget": self.cluster_budget if self.training else None,
-                   # weight gradients of a bidirectional stack (the target encoder) and of a unidirectional one (source
-                   # encoder / decoder) go to different side streams: the two encoders' backward passes run
-                   # concurrently and their last weight-gradient blocks are the tail of the step
-                   "side_lane": 1 if self.bidirectional else 0,
+                   # weight gradients of a bidirectional stack (the target encoder: lanes 2 + direction) and of a
+                   # unidirectional one (source encoder / decoder: lane = layer parity) go to different side streams: the
+                   # two encoders' backward passes run concurrently and their last weight-gradient blocks are the tail of
+                   # the step
+                   "side_lane": 2 if self.bidirectional else l % 2,
                    "fires_early_exchange": self.fires_early_exchange}
             x, hT, cT = ops.lstm_layer(x, h0, c0, in_bias if l == 0 else None, lengths, cfg, self._weights(l))
             hs.append(hT)

@@ -121,7 +121,8 @@ def _anchor(device):
 # themselves: two of them may accumulate into slices of the same parameter) that forks from the main stream after
 # the tensors they read are complete, and is joined before the gradients are consumed (end of the backward pass /
 # Optim.step).  Under CUDA-graph capture the fork / join become graph edges.
-_side = {"streams": [], "keep": [], "dirty": False, "enabled": True, "next": 0, "lanes": 2}
+_side = {"streams": [], "keep": [], "dirty": False, "enabled": True, "next": 0,
+         "lanes": int(os.environ.get("VMMT_SIDE_LANES", "4"))}
 
 
 def set_side_stream_enabled(flag):
@@ -218,7 +219,8 @@ class branch(object):
         cur = torch.cuda.current_stream()
         st = _branch["streams"].get(self.lane)
         if st is None or st.device != cur.device:
-            st = _branch["streams"][self.lane] = torch.cuda.Stream(device=cur.device, priority=-1)
+            st = _branch["streams"][self.lane] = torch.cuda.Stream(
+                device=cur.device, priority=int(os.environ.get("VMMT_BRANCH_PRIO", "-1")))
         st.wait_stream(cur)
         self.ctx = torch.cuda.stream(st)
         self.ctx.__enter__()
@@ -707,8 +709,8 @@ class LSTMLayerFn(Function):
             for d in range(ndir):                                          # the term enters every direction
                 colsum_acc(dg[d].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
         # weight / bias gradients (side stream): they only feed the optimiser
-        with on_side(dg, x, out, h0, lane=ctx.side_lane):
-            for d in range(ndir):
+        for d in range(ndir):                                                 # one block (= one lane) per direction
+            with on_side(dg, x, out, h0, lane=None if ctx.side_lane is None else ctx.side_lane + d):
                 w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
                 dg2 = dg[d].view(T * N, 4 * Hd)
                 if w_ih.requires_grad and not gx_given:                    # dW_ih += dG^T x
