@@ -6,6 +6,7 @@ import torch
 from variational_mmt_b200 import _lib
 from variational_mmt_b200.ops import fptr, ptr, stream
 M, H, V = [int(x) for x in sys.argv[1:4]]
+FLAGS = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # 2 = bf16 operands
 dev = "cuda"
 x = torch.randn(M, H, device=dev) * 0.5
 W = (torch.rand(V, H, device=dev) - 0.5) * 0.2
@@ -17,6 +18,6 @@ wsb = _lib.lib.vmmt_generator_workspace_bytes(M, H, V)
 ws = torch.empty(wsb // 4, device=dev)
 for _ in range(3):
     _lib.call("vmmt_generator_nll_fwd", fptr(x), fptr(W), fptr(b), ptr(tgt), 1, M, H, V, fptr(lse), fptr(stats),
-              fptr(ws), wsb, 0, stream())
+              fptr(ws), wsb, FLAGS, stream())
 torch.cuda.synchronize()
 print("ok", stats.tolist())

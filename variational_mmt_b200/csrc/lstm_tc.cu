@@ -11,20 +11,26 @@
 //     the same 11 significand bits as TF32, which is what a tensor-core "fp32" GEMM rounds its operands to;
 //     accumulation is fp32 in TMEM; c / h state stays fp32 in registers, h is rounded to fp16 only as the next
 //     step's MMA operand.
-//   * forward step : D[128 gate rows, 16 batch cols] = W_slice[128,Kp] * h_{t-1}^T  (Kp/16 tcgen05.mma M128 N16 K16,
-//                    four independent accumulator chains) -> tcgen05.ld -> gates regrouped through shared memory ->
-//                    sigmoid/tanh cell update fused in the epilogue -> the CTA's new fp16 h slice (1 KB, contiguous in
-//                    the un-swizzled K-major operand tile) goes to every CTA of the cluster as ONE bulk async copy
-//                    per destination (cp.async.bulk shared::cta -> shared::cluster) that completes on the
-//                    destination's mbarrier.  The MMA warp of each CTA waits on that mbarrier only: producer ->
-//                    consumer data flow replaces the barrier, and both ends of the hand-off are in the async proxy.
+//   * forward step : D[128 gate rows, 8 or 16 batch cols] = W_slice[128,Kp] * h_{t-1}^T  (Kp/16 tcgen05.mma M128 K16 with the
+//                    A operand in TMEM, independent accumulator chains per row group) -> 8 epilogue warps drain the
+//                    accumulator (tcgen05.ld) -> gates regrouped through a double-buffered shared-memory tile ->
+//                    sigmoid/tanh cell update fused in the epilogue (cell (n = warp + 8 r, unit = lane); pinned
+//                    __fmaf_rn / __fadd_rn arithmetic so that the 8-row and 16-row instantiations round alike) -> the
+//                    new fp16 h values are packed 8 lanes -> 16 bytes by shuffles and sent with st.async (16 B,
+//                    mbarrier::complete_tx) straight from registers into the K-major operand tile of EVERY CTA of the
+//                    cluster; the next step's gx[t+1] is prefetched meanwhile.  The MMA warp of each CTA waits on the
+//                    tile's mbarrier only (expect_tx = C * rows * 64 bytes): producer -> consumer data flow replaces a
+//                    cluster barrier; the consumer issues fence.proxy.async before the MMA reads the tile.
 //   * backward step: the SAME slice transposed (A = W_slice^T, resident in TMEM): each CTA contracts its own 128
 //                    gate rows, partial dh[512 units, batch] = W_slice^T * dG_t^T (dG enters as fp16 hi + lo columns
 //                    of dG * 2^12: 22 significand bits, no gradient magnitude is lost); the partials are
-//                    reduce-scattered to the unit owners with one 2 KB bulk copy per owner, again signalled through
-//                    mbarriers, and summed in a fixed order (deterministic).
+//                    reduce-scattered to the unit owners with one bulk copy per PEER owner (cp.async.bulk
+//                    shared::cta -> shared::cluster, completing on the owner's mbarrier; the CTA's own block is read
+//                    from its staging buffer) and summed in a fixed order (deterministic).
 // Double buffering + the data dependence of the recurrence itself make every buffer reuse safe (see the comments
-// at the copies).
+// at the copies); compute-sanitizer memcheck / racecheck / synccheck are clean (profiles/sanitizer_*_r2.txt).
+// Measured per step at H = 500, 8 rows per cluster (ncu launch list, profiles/launches_r2_summary.txt): 1.8 us forward,
+// 2.4 us backward; VMMT_LSTM_FLOOR=1 runs the hand-off chain without the cell arithmetic (the measured floor bench.py reports).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
