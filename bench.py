@@ -822,7 +822,7 @@ def roofline_generator(args, mk, bk, shard, model, peaks, how, vm, _lib, dev):
     peak = peaks["bf16_tflops"] / (1.0 if args.dtype == "bf16" else 2.0)       # TF32 runs at half the bf16 tensor rate
     name = "vmmt_generator_nll_fwd (M=%d,H=%d,V=%d)" % (M, H, V)
     traffic = None                           # DRAM bytes per launch from the committed `ncu --set full` capture, if any
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = (json.load(f).get(name) or {}).get("dram_bytes")

@@ -176,6 +176,7 @@ struct GemmArgs {
   int topk;                     // mode 3
   float2* tile_lse;             // mode 3: [tiles_n][M] {max, sum exp}
   float2* tile_cand;            // mode 3: [tiles_n][M][topk] {logit, column}
+  int group_m;                  // row-tiles per rasterisation group (see tile_origin)
 };
 
 template <int ACT>
@@ -427,9 +428,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // Tile rasterisation: tiles are numbered so that consecutive ones walk DOWN a group of GROUP_M row-tiles before moving
   // to the next column-tile: the ~148 co-resident CTAs share GROUP_M A-tiles and ~10 B-tiles out of L2 instead of one
   // A-tile and 148 B-tiles (the generator's [V,H] weight is larger than L2 at cfg5: without this every row-tile sweep
-  // re-read all of it from HBM -- 39 GB of DRAM traffic for 0.3 GB of operands).
+  // re-read all of it from HBM -- 39 GB of DRAM traffic for 0.3 GB of operands).  The group's A panel (GROUP_M x 128 rows x
+  // K) has to stay L2-resident while B streams past it once per group: 64 row-tiles when K is small enough for a
+  // <= 48 MB panel (generator forward: B re-read 5 x instead of 20 x at cfg5), 16 otherwise (host side: group_m).
   auto tile_origin = [&](int lin, int& m0, int& n0) {
-    constexpr int GROUP_M = 16;
+    const int GROUP_M = g.group_m;
     const int grp = lin / (GROUP_M * g.tiles_n);
     const int first_m = grp * GROUP_M;
     const int gm = min(GROUP_M, g.tiles_m - first_m);
@@ -799,7 +802,12 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
     if (rc) return rc;
   }
   GemmArgs g{C, ldc, M, N, K, bias, finish_act ? VMMT_ACT_NONE : act, accumulate, kb_per, tma_store, dbg, tiles_m, ceil_div(N, BN), nkb2, nullptr,
-             0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, 0, nullptr, nullptr};
+             0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f, 0, 0, nullptr, nullptr, 16};
+  {
+    static const int forced = getenv("VMMT_GEMM_GROUP_M") ? atoi(getenv("VMMT_GEMM_GROUP_M")) : 0;
+    const size_t panel64 = (size_t)64 * BM * (size_t)(K + (second ? second->K2 : 0)) * (bf ? 2 : 4);
+    g.group_m = forced > 0 ? forced : (panel64 <= ((size_t)48 << 20) ? 64 : 16);
+  }
   if (epi) {
     g.epi_mode = epi->mode;
     g.lse_part = reinterpret_cast<float4*>(epi->lse_part);
