@@ -37,6 +37,9 @@ unsigned long long vmmt_launch_count(void);
 #define VMMT_F_BF16 2        /* tensor-core contractions on bf16 operands (fp32 accumulate) instead of TF32 */
 #define VMMT_F_BACKGROUND 4  /* optimiser-only work (weight gradients on a low-priority side stream): one tile per CTA instead
                                 of the persistent per-SM tile loop, so that SMs free up for critical-path kernels between tiles */
+#define VMMT_F_SHARE_SMS 16  /* a LARGE optimiser-only GEMM (more tiles than SMs) issued while short critical-path kernels run and no
+                                recurrence cluster is waiting: persistent tile loop on 5/18 of the SMs (41 of 148), so that the critical chain
+                                always finds free SMs (a grid that fills every SM makes later launches wait a whole tile time) */
 #define VMMT_F_NO_SPLITK 8   /* one accumulation chain per output element in fixed K order: run-to-run deterministic and
                                 batch-invariant (a row's result does not depend on how many rows the call has) */
 

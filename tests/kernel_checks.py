@@ -157,7 +157,10 @@ def check_attention(tol=2e-5):
     from variational_mmt_b200 import ops
     from oracle import vi_model1_ref as R
     out = []
-    for (T, B, S, H) in [(31, 40, 30, 500), (9, 5, 11, 64), (1, 200, 17, 500), (3, 2, 70, 36)]:
+    # (.., 80, 1024): 3 source blocks x 2 contraction chunks of the v2 kernel; (17, 4, 50, 512): 2 position groups x 2 query
+    # shares in the context gradient; (33, 2, 128, 96): the maximum source length; (5, 3, 33, 130): H % 4 != 0 -> v1 kernels
+    for (T, B, S, H) in [(31, 40, 30, 500), (9, 5, 11, 64), (1, 200, 17, 500), (3, 2, 70, 36), (20, 3, 80, 1024),
+                         (17, 4, 50, 512), (33, 2, 128, 96), (5, 3, 33, 130), (16, 2, 32, 512), (2, 1, 1, 4)]:
         qp = _r(T, B, H, scale=0.3, seed=41).requires_grad_(True)
         ctx = _r(S, B, H, scale=0.3, seed=42).requires_grad_(True)
         lengths = torch.randint(1, S + 1, (B,), generator=torch.Generator().manual_seed(5))

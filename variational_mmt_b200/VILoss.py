@@ -186,8 +186,9 @@ class NMTVIModel1LossCompute(nn.Module):
         batch_stats = VIStatistics(self.multimodal_model_type)
         range_ = (cur_trunc, cur_trunc + trunc_size)
         state = self._make_shard_state(batch, output, range_, attns)
-        state["output"] = state["output"][:shard_size]
-        state["target"] = state["target"][:shard_size]
+        if state["output"].size(0) > shard_size:           # (a no-op slice would still cost a zero-fill + copy in backward)
+            state["output"] = state["output"][:shard_size]
+            state["target"] = state["target"][:shard_size]
         loss, stats = self._compute_loss(batch, **state)
         hook = getattr(self, "before_backward", None)      # GraphedTrainStep: join the gradient memset issued beside the loss
         if hook is not None:

@@ -116,7 +116,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SOFTPLUS, ACT_SIGMOID = range(5)
-F_EXACT, F_BF16, F_BACKGROUND, F_NO_SPLITK = 1, 2, 4, 8          # include/vmmt.h VMMT_F_*
+F_EXACT, F_BF16, F_BACKGROUND, F_NO_SPLITK, F_SHARE_SMS = 1, 2, 4, 8, 16          # include/vmmt.h VMMT_F_*
 
 
 def last_error():

@@ -10,6 +10,7 @@
 // copies (GlobalAttention.py:204-205) disappear.  One warp per query (t,b); the context rows of
 // one batch element stay L1/L2 resident across the queries of that element.
 #include <stdlib.h>
+#include <mutex>
 #include "common.cuh"
 #include "vmmt_internal.h"
 
@@ -361,16 +362,23 @@ attn_bwd_query_tiled_kernel(const float* __restrict__ dc, const float* __restric
 }
 
 // backward, stage 2 per (b, 64 hidden units): dctx[j,b,k] (+)= sum_t ( a[t,b,j] dc[t,b,k] + ds[t,b,j] qp[t,b,k] )
-// thread (k = k0 + tid % 64, jg = tid / 64) owns the contiguous block of JB source positions jg*JB .. jg*JB+JB-1
+// thread (k = k0 + tid % 64, g = tid / 64): the four 64-thread groups split the work as (position group of 32) x (share of
+// the queries): S <= 32 -> one position group, each thread group takes every 4th query and the partial sums are added in a
+// fixed order through shared memory; S <= 64 -> 2 x 2; longer sources -> 4 position groups x all queries.  (With the
+// position groups alone, three quarters of the CTA idled at the S = 30 of a Multi30k batch.)
 __global__ void __launch_bounds__(TILE_THREADS)
 attn_bwd_ctx_tiled_kernel(const float* __restrict__ dc, const float* __restrict__ qp, const float* __restrict__ align,
                           const float* __restrict__ dscore, float* __restrict__ dctx, int T, int B, int S, int H,
                           int accumulate, int nk) {
   __shared__ __align__(16) float As[TT][SMAX];
   __shared__ __align__(16) float Ds[TT][SMAX];
-  const int b = blockIdx.x / nk, k = (blockIdx.x % nk) * 64 + (threadIdx.x & 63);
-  const int jg = threadIdx.x >> 6;
-  constexpr int JB = SMAX / 4;                       // 32 positions per thread group (covers S <= 128)
+  constexpr int JB = SMAX / 4;                       // 32 positions per position group (covers S <= 128)
+  __shared__ float Red[3][JB][64];                   // partial sums of the query shares 1..3
+  const int b = blockIdx.x / nk, kk = threadIdx.x & 63, k = (blockIdx.x % nk) * 64 + kk;
+  const int g = threadIdx.x >> 6;
+  const int pg = (S + JB - 1) / JB;                  // position groups in use: 1..4
+  const int ts = (pg == 1) ? 4 : (pg == 2 ? 2 : 1);  // query shares
+  const int jg = (ts == 1) ? g : g % pg, tsi = (ts == 1) ? 0 : g / pg;
   float acc[JB];
 #pragma unroll
   for (int i = 0; i < JB; ++i) acc[i] = 0.f;
@@ -385,7 +393,7 @@ attn_bwd_ctx_tiled_kernel(const float* __restrict__ dc, const float* __restrict_
     }
     __syncthreads();
     const int tn = min(TT, T - t0);
-    for (int tt = 0; tt < tn; ++tt) {
+    for (int tt = tsi; tt < tn; tt += ts) {
       const size_t row = ((size_t)(t0 + tt) * B + b) * H;
       const float dcv = k < H ? __ldg(dc + row + k) : 0.f, qv = k < H ? __ldg(qp + row + k) : 0.f;
       const float4* a4 = reinterpret_cast<const float4*>(&As[tt][jg * JB]);
@@ -402,6 +410,18 @@ attn_bwd_ctx_tiled_kernel(const float* __restrict__ dc, const float* __restrict_
       }
     }
   }
+  if (ts > 1) {                                      // block-uniform
+    if (tsi > 0) {
+#pragma unroll
+      for (int i = 0; i < JB; ++i) Red[(tsi - 1) * pg + jg][i][kk] = acc[i];
+    }
+    __syncthreads();
+    if (tsi > 0) return;
+    for (int x = 0; x < ts - 1; ++x) {
+#pragma unroll
+      for (int i = 0; i < JB; ++i) acc[i] += Red[x * pg + jg][i][kk];
+    }
+  }
   if (k < H) {
 #pragma unroll
     for (int i = 0; i < JB; ++i) {
@@ -412,6 +432,210 @@ attn_bwd_ctx_tiled_kernel(const float* __restrict__ dc, const float* __restrict_
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 of the (sentence, 16-query tile) kernels -- forward (MODE 0: P = qp ctx^T -> softmax -> c = a ctx) and the query side
+// of the backward (MODE 1: P = dc ctx^T -> ds = a (P - sum a P) -> dqp = ds ctx).  The v1 kernels above staged 32-wide
+// contraction chunks through registers and issued 3 LDS per 2 FMA: 12 K instructions per warp, issue-bound at 31 us for
+// 0.07 GFLOP (ncu, cfg1 shape).  Here
+//   * the whole 16 x KP query tile and 32 x KP context block (KP <= 512 floats of the contraction) are brought into shared
+//     memory with ONE burst of 16-byte cp.async (one global-latency exposure per block instead of one per chunk),
+//   * the contraction is split over the 8 warps ALONG K; each lane owns a 4 x 4 block of the 16 x 32 score tile and reads
+//     4 + 4 float4 per 64 FMA (rows 4 banks apart: conflict-free LDS.128), the 8 partial tiles are summed in warp order
+//     through shared memory (deterministic),
+//   * the second contraction reads the context block it already holds in shared memory (when S <= 32 and H <= 512;
+//     longer sources / wider layers loop over blocks and re-read the context from L2).
+// Needs H % 4 == 0 and 16-byte aligned operands (else v1).  Arithmetic stays exact fp32.
+constexpr int V2_KCH = 512;
+constexpr int V2_PS = 40;          // partial-tile row stride: bank = 8 * (row % 4) + col % 8 over a warp's 32 lanes
+
+__device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void att_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void att_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+size_t v2_smem_bytes(int KP) {
+  return (size_t)(48 * (KP + 4) + 8 * 16 * V2_PS + 16 * (SMAX + 4) + SMAX * TT) * sizeof(float);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS)
+attn_v2_kernel(const float* __restrict__ X, const float* __restrict__ ctx, const int64_t* __restrict__ lengths,
+               float* __restrict__ align, float* __restrict__ dscore, float* __restrict__ out, int T, int B, int S, int H,
+               int ntile, int KP) {
+  extern __shared__ __align__(16) float att_smem[];
+  const int ST = KP + 4;                             // row stride: 16-byte aligned, consecutive rows 4 banks apart
+  float* Xs = att_smem;                              // [16][ST]
+  float* Cs = Xs + 16 * ST;                          // [32][ST]
+  float* Pp = Cs + 32 * ST;                          // [8 warps][16][V2_PS]
+  float* Pf = Pp + 8 * 16 * V2_PS;                   // [16][SMAX + 4] scores of the whole source
+  float* Ws = Pf + 16 * (SMAX + 4);                  // [SMAX][16] weights, query index fastest
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / ntile, t0 = (blockIdx.x % ntile) * TT;
+  const int len = lengths ? min((int)lengths[b], S) : S;
+  const int nsb = (S + 31) / 32, nkc = (H + KP - 1) / KP;
+  const int rg = lane >> 3, cg = lane & 7;           // this lane's rows rg + 4 i, columns cg + 8 i
+  const int KQ = KP / 4;                             // float4 per staged row
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sb = 0; sb < nsb; ++sb) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int i2 = 0; i2 < 4; ++i2) acc[i][i2] = 0.f;
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int k0 = kc * KP, kl = min(KP, H - k0);  // valid floats of this chunk (multiple of 4)
+      __syncthreads();                               // the previous block / chunk has been consumed
+      if (nkc > 1 || sb == 0) {
+        for (int e = tid; e < 16 * KQ; e += TILE_THREADS) {
+          const int r = e / KQ, k = (e % KQ) * 4, t = t0 + r;
+          float* dst = Xs + r * ST + k;
+          if (t < T && k < kl) att_cp_async16(att_smem_u32(dst), X + ((size_t)t * B + b) * H + k0 + k);
+          else *reinterpret_cast<float4*>(dst) = zero4;
+        }
+      }
+      for (int e = tid; e < 32 * KQ; e += TILE_THREADS) {
+        const int r = e / KQ, k = (e % KQ) * 4, j = sb * 32 + r;
+        float* dst = Cs + r * ST + k;
+        if (j < S && k < kl) att_cp_async16(att_smem_u32(dst), ctx + ((size_t)j * B + b) * H + k0 + k);
+        else *reinterpret_cast<float4*>(dst) = zero4;
+      }
+      att_cp_async_wait_all();
+      __syncthreads();
+      const float* xb = Xs + rg * ST + warp * (KP / 8);
+      const float* cb = Cs + cg * ST + warp * (KP / 8);
+#pragma unroll 2
+      for (int kk = 0; kk < KP / 8; kk += 4) {
+        float4 xv[4], cv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xb + 4 * i * ST + kk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cv[i] = *reinterpret_cast<const float4*>(cb + 8 * i * ST + kk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            acc[i][i2] = fmaf(xv[i].x, cv[i2].x, acc[i][i2]);
+            acc[i][i2] = fmaf(xv[i].y, cv[i2].y, acc[i][i2]);
+            acc[i][i2] = fmaf(xv[i].z, cv[i2].z, acc[i][i2]);
+            acc[i][i2] = fmaf(xv[i].w, cv[i2].w, acc[i][i2]);
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int i2 = 0; i2 < 4; ++i2) Pp[(warp * 16 + rg + 4 * i) * V2_PS + cg + 8 * i2] = acc[i][i2];
+    __syncthreads();
+    for (int e = tid; e < 16 * 32; e += TILE_THREADS) {
+      const int r = e >> 5, c = e & 31;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += Pp[(w * 16 + r) * V2_PS + c];
+      Pf[r * (SMAX + 4) + sb * 32 + c] = sum;
+    }
+    // (Pp is rewritten only after the next block's staging barriers)
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int tt = 2 * warp + i, t = t0 + tt;
+    float v[4];
+    if (MODE == 0) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        v[jj] = (j < len) ? Pf[tt * (SMAX + 4) + j] : -INFINITY;
+        mx = fmaxf(mx, v[jj]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) { v[jj] = expf(v[jj] - mx); sum += v[jj]; }   // exp(-inf) = 0
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) v[jj] *= inv;
+    } else {
+      float a[4], dot = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        a[jj] = (t < T && j < len) ? align[((size_t)t * B + b) * S + j] : 0.f;
+        v[jj] = (j < len) ? Pf[tt * (SMAX + 4) + j] : 0.f;
+        dot = fmaf(a[jj], v[jj], dot);
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) v[jj] = a[jj] * (v[jj] - dot);
+    }
+    float* gout = (MODE == 0) ? align : dscore;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < nsb * 32) Ws[j * TT + tt] = v[jj];
+      if (t < T && j < S) gout[((size_t)t * B + b) * S + j] = v[jj];
+    }
+  }
+  __syncthreads();
+  if (nsb == 1 && nkc == 1) {                        // the context block is still resident
+    for (int k = tid; k < H; k += TILE_THREADS) {
+      float o[TT];
+#pragma unroll
+      for (int i = 0; i < TT; ++i) o[i] = 0.f;
+      for (int j = 0; j < len; ++j) {
+        const float c = Cs[j * ST + k];
+        const float4* w4 = reinterpret_cast<const float4*>(Ws + j * TT);
+#pragma unroll
+        for (int q = 0; q < TT / 4; ++q) {
+          const float4 w = w4[q];
+          o[4 * q] = fmaf(w.x, c, o[4 * q]); o[4 * q + 1] = fmaf(w.y, c, o[4 * q + 1]);
+          o[4 * q + 2] = fmaf(w.z, c, o[4 * q + 2]); o[4 * q + 3] = fmaf(w.w, c, o[4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TT; ++i)
+        if (t0 + i < T) out[((size_t)(t0 + i) * B + b) * H + k] = o[i];
+    }
+  } else {
+    wv_tile(reinterpret_cast<const float (*)[TT]>(Ws), ctx, out, t0, T, b, B, len, H);
+  }
+}
+
+// Used where it wins: H <= 512 (one contraction chunk) and S <= 64 (at most two source blocks).  Measured at the cfg5
+// shape (T = S = 80, H = 1024, B = 512: 3 blocks x 2 chunks, each with its own staging barriers and one CTA per SM) v2 is
+// 18 % slower than the register-staged v1 kernels (1.19 vs 1.01 ms forward); at cfg1 (S = 30, H = 500) 19 vs 34 us.
+bool v2_ok(const void* a, const void* b, int T, int S, int H) {
+  return T > 1 && H <= V2_KCH && S <= 64 && (H & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0 &&
+         !getenv("VMMT_ATTN_V1");
+}
+
+template <int MODE>
+int launch_v2(const float* X, const float* ctx, const int64_t* lengths, float* align, float* dscore, float* out, int T,
+              int B, int S, int H, cudaStream_t st) {
+  const int KP = min(V2_KCH, ((H + 31) / 32) * 32);
+  const size_t smem = v2_smem_bytes(KP);
+  {
+    static std::mutex mu;                                    // function attributes are sticky: once per device
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+      VMMT_CUDA(cudaFuncSetAttribute(attn_v2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)v2_smem_bytes(V2_KCH)));
+      done[dev] = true;
+    }
+  }
+  const int ntile = ceil_div(T, TT);
+  attn_v2_kernel<MODE><<<B * ntile, TILE_THREADS, smem, st>>>(X, ctx, lengths, align, dscore, out, T, B, S, H, ntile, KP);
+  return vmmt_check_launch(MODE == 0 ? "attn_v2_kernel<fwd>" : "attn_v2_kernel<bwd>");
 }
 
 size_t tiled_smem_bytes(int S) {
@@ -426,6 +650,8 @@ extern "C" int vmmt_attention_fwd(const float* qp, const float* ctx, const int64
                                   void* stream) {
   VMMT_REQUIRE(S >= 1 && S <= SMAX, "attention_fwd: src_len %d outside [1,%d]", S, SMAX);
   VMMT_REQUIRE(T >= 1 && B >= 1 && H >= 1, "attention_fwd: bad dims");
+  if (v2_ok(qp, ctx, T, S, H) && !getenv("VMMT_ATTN_WARP"))
+    return launch_v2<0>(qp, ctx, lengths, align, nullptr, cvec, T, B, S, H, (cudaStream_t)stream);
   if (T > 1 && !getenv("VMMT_ATTN_WARP")) {          // sequence mode: tiled kernel (one CTA per 16 queries of one row)
     const int ntile = ceil_div(T, TT);
     attn_fwd_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), (cudaStream_t)stream>>>(
@@ -449,9 +675,14 @@ extern "C" int vmmt_attention_bwd(const float* dcvec, const float* qp, const flo
   if (!getenv("VMMT_ATTN_WARP")) {
     cudaStream_t st = (cudaStream_t)stream;
     const int ntile = ceil_div(T, TT), nk = ceil_div(H, 64);
-    attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), st>>>(dcvec, ctx, align, lengths,
-                                                                                      dscore_ws, dqp, T, B, S, H, ntile);
-    int rc1 = vmmt_check_launch("attn_bwd_query_tiled_kernel");
+    int rc1;
+    if (v2_ok(dcvec, ctx, T, S, H) && (reinterpret_cast<uintptr_t>(dqp) & 15) == 0) {
+      rc1 = launch_v2<1>(dcvec, ctx, lengths, const_cast<float*>(align), dscore_ws, dqp, T, B, S, H, st);
+    } else {
+      attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), st>>>(dcvec, ctx, align, lengths,
+                                                                                        dscore_ws, dqp, T, B, S, H, ntile);
+      rc1 = vmmt_check_launch("attn_bwd_query_tiled_kernel");
+    }
     if (rc1) return rc1;
     attn_bwd_ctx_tiled_kernel<<<B * nk, TILE_THREADS, 0, st>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H,
                                                                accumulate_dctx, nk);

@@ -734,6 +734,7 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
                       const VmmtGenEpi* epi, const VmmtGemmSecond* second, int flags, cudaStream_t s) {
   const bool a_mn = !a_kmajor, b_mn = !b_kmajor;
   const bool background = (flags & VMMT_F_BACKGROUND) != 0;
+  const bool share = (flags & VMMT_F_SHARE_SMS) != 0;
   // VMMT_F_BF16 on this INTERNAL entry point: A / B (and the second pair) point to bf16 data, lda / ldb count bf16
   // elements (vmmt_gemm_bf16 and the generator's bf16 path cast the fp32 tensors first)
   const bool bf = (flags & VMMT_F_BF16) != 0;
@@ -748,7 +749,7 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   // 64-wide tiles two per SM; split-K needs a linear epilogue (an activation is applied by a finishing pass)
   // VMMT_F_NO_SPLITK: one accumulation chain per output element in fixed K order (deterministic; a row's result does not
   // depend on how many rows the call has: inference compares a sentence decoded alone with the same sentence in a batch)
-  const bool can_split = !(flags & VMMT_F_NO_SPLITK) && epi == nullptr && second == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
+  const bool can_split = !(flags & VMMT_F_NO_SPLITK) && !share && epi == nullptr && second == nullptr && ((accumulate == 0) || (accumulate == 1 && bias == nullptr && act == VMMT_ACT_NONE));
   int BN = 128, splits = 1;
   double best = 1e30;
   for (int bn = (epi ? 128 : 64); bn <= 128; bn *= 2) {
@@ -830,7 +831,9 @@ int vmmt_gemm_tc_dual(const float* A, int64_t lda, int a_kmajor, const float* B,
   // its SM for the whole GEMM, and a recurrence kernel launched meanwhile cannot place its 16-CTA clusters until the GEMM
   // ends (measured: +80..100 us on an encoder layer's backward, at random); short-lived CTAs drain within one tile time
   // and the higher-priority cluster launch gets the SMs.
-  dim3 grid((splits > 1 || no_persist || background) ? tiles : min(tiles, slots), 1, splits);
+  static const int share_slots = getenv("VMMT_GEMM_SHARE_SLOTS") ? atoi(getenv("VMMT_GEMM_SHARE_SLOTS")) : 0;
+  dim3 grid(share ? min(tiles, share_slots > 0 ? share_slots : max(1, nsm * 5 / 18))
+                  : ((splits > 1 || no_persist || background) ? tiles : min(tiles, slots)), 1, splits);
   static long long* trace_buf = nullptr;
   const bool tracing = getenv("VMMT_GEMM_TRACE") != nullptr;
   if (tracing) {

@@ -979,8 +979,13 @@ class VILossFn(Function):
         L.call("vmmt_generator_nll_bwd", fptr(out2d), fptr(ctx.gen_w), fptr(ctx.gen_b), ptr(target),
                cfg["pad_idx"], fptr(lse), fptr(gs), 1.0, M, H, V, fptr(dx), None, None, fptr(ws), wsb, flags(), stream())
         with on_side(ws, out2d):                               # generator weight gradient: off the critical path
+            # the one weight-gradient GEMM with more tiles than SMs (V/128 x H/128): it starts when the decoder-output
+            # gradient is done, i.e. together with the short kernels that lead to the decoder's backward recurrence
+            # (measured: with every SM holding one of its CTAs those kernels waited 38 us for the first wave to retire)
+            # (a cfg5-sized product, 2.6 TFLOP, keeps the one-tile-per-CTA background form: it would hold its share for ms)
+            share = L.F_SHARE_SMS if (2.0 * M * H * V < 5e10 and os.environ.get("VMMT_GEN_WGRAD_SHARE", "1") != "0") else 0
             L.call("vmmt_generator_nll_wgrad", fptr(out2d), fptr(ws), M, H, V, fptr(grad_buf(ctx.gen_w)),
-                   fptr(grad_buf(ctx.gen_b)), flags(), stream())
+                   fptr(grad_buf(ctx.gen_b)), flags() | share, stream())
         cur.wait_stream(_loss_stream)
         return dx, None, None, None, dmq, dsq, dmp, dsp, dloc, None, None
 
