@@ -187,7 +187,9 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
                 dec_gx = self.decoder.input_projection(tgt)
         if self.conditional:
             assert isinstance(self.inf_net_global, GlobalFullInferenceNetwork)
-            with ops.branch():                                                   # p(z|x): only the KL needs it in training
+            # p(z|x): only the KL needs it in training -> the low-priority lane (its row-block kernels, forward and backward,
+            # must not queue ahead of the critical chain's short kernels in the block scheduler)
+            with ops.branch(lane=ops.LOW_LANE if self.training else 0):
                 pz0, _ = self.gen_net_global(context, lengths)
             if not self.training:
                 ops.join_branch(pz0.mean())
@@ -199,7 +201,7 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             z0_sample = z0.sample() if self.training else z0.mean().detach()
             pz0 = Normal(torch.zeros_like(z0.params()[0]), torch.ones_like(z0.params()[0]))
             pz0.is_standard = True
-        with ops.branch():                                                       # p(v|z) beside the decoder
+        with ops.branch(lane=ops.LOW_LANE):                                      # p(v|z) beside the decoder: only the loss needs it
             p_v, _ = self.inf_net_image(z0_sample, context, lengths)
         enc_state = self.decoder.init_decoder_state(src, context, enc_hidden)
         extra = {}
@@ -208,7 +210,7 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             extra["input_projection"] = dec_gx
         out, dec_state, attns = self.decoder(tgt, context, enc_state if dec_state is None else dec_state,
                                              lengths, image_features=None, z_sample=z0_sample, **extra)
-        ops.join_branch(p_v.mean(), *([] if getattr(pz0, "is_standard", False) else pz0.params()))
+        ops.join_branch(p_v.mean(), *([] if getattr(pz0, "is_standard", False) else pz0.params()), lane=ops.LOW_LANE)
         attns["p_global_image_features"] = [p_v]
         attns["ground_truth_global_image_features"] = [img_feats]
         attns["p_latent"] = [pz0]

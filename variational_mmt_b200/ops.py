@@ -200,14 +200,16 @@ def join_side():
 # ---- branch stream: independent sub-graphs of the forward pass (and, through autograd's per-node streams, of the
 # backward pass) run beside the main chain: prior network and image-feature head beside the decoder ----------------
 _branch = {"streams": {}, "enabled": True}
+LOW_LANE = 3          # branch lane for sub-graphs nothing on the critical chain waits for: lowest stream priority
 
 
 class branch(object):
     """``with ops.branch(): ...`` issues the enclosed module calls on a branch stream, ordered after everything
     already on the current stream.  Autograd nodes created inside remember that stream, so their backward runs
     there too.  ``ops.join_branch(*tensors)`` makes the current stream wait and hands the tensors over.
-    ``lane`` selects one of several branch streams (0: encoder / prior / image head beside the main chain,
-    1: the scale MLP of the posterior beside its location MLP); blocks may nest across lanes."""
+    ``lane`` selects one of several branch streams (0: target encoder beside the source encoder, 1: the scale MLP of the
+    posterior beside its location MLP, 2: the decoder's input projection, LOW_LANE: prior network and image head -- only
+    the loss reads them); blocks may nest across lanes."""
 
     def __init__(self, lane=0):
         self.lane = lane
@@ -219,8 +221,9 @@ class branch(object):
         cur = torch.cuda.current_stream()
         st = _branch["streams"].get(self.lane)
         if st is None or st.device != cur.device:
-            st = _branch["streams"][self.lane] = torch.cuda.Stream(
-                device=cur.device, priority=int(os.environ.get("VMMT_BRANCH_PRIO", "-1")))
+            prio = int(os.environ.get("VMMT_BRANCH_LOW_PRIO", "0")) if self.lane == LOW_LANE \
+                else int(os.environ.get("VMMT_BRANCH_PRIO", "-1"))
+            st = _branch["streams"][self.lane] = torch.cuda.Stream(device=cur.device, priority=prio)
         st.wait_stream(cur)
         self.ctx = torch.cuda.stream(st)
         self.ctx.__enter__()
