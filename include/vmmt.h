@@ -129,10 +129,12 @@ int vmmt_attention_bwd(const float* dcvec, const float* qp, const float* ctx, co
                        int accumulate_dctx, int T, int B, int S, int H, void* stream);
 
 /* ---- inference networks (NormalVariationalEncoder.py:65-84, 12-43; Dists.py:21-26; VILoss.py:439-460) */
-int vmmt_masked_mean_fwd(const float* x, const int64_t* lengths, float* out, int64_t out_ld, int T, int B,
-                         int H, void* stream);
-int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* lengths, float* dx,
-                         int accumulate, int T, int B, int H, void* stream);
+/* x[t,b,k] at x + t*stride_t + b*stride_b + k: time-major [T,B,H] (stride_t = B*H, stride_b = H) or the transposed view of a
+ * [B,T,H] tensor (stride_t = H, stride_b = T*H: the target encoder's output, Models.py:905-911, without a transposing copy) */
+int vmmt_masked_mean_fwd(const float* x, int64_t stride_t, int64_t stride_b, const int64_t* lengths, float* out,
+                         int64_t out_ld, int T, int B, int H, void* stream);
+int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* lengths, float* dx, int64_t stride_t,
+                         int64_t stride_b, int accumulate, int T, int B, int H, void* stream);
 int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
 /* stats8 = {nll, n_words, n_correct, kl, img_logprob, img_cos, -, -}: writes loss1[0] = stats8[7] = nll - img_logprob +
  * kl_weight * kl and stats8[6] = kl_weight * kl (VILoss.py:462-496) in one launch. */
@@ -143,6 +145,9 @@ int vmmt_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
 /* Philox streams: effective offset = offset + (base ? *base : 0); `base` is a device-resident counter so that a
  * captured CUDA graph draws fresh masks / noise on every replay (advance it with vmmt_counter_add). */
 int vmmt_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
+/* debug / measurement: buf[slot] = %globaltimer (ns) when the stream reaches this point (a one-thread kernel: phase
+ * boundaries of a captured step without a profiler attached, tools/phase_stamps.py) */
+int vmmt_stamp(uint64_t* buf, int slot, void* stream);
 int vmmt_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
                  const uint64_t* base /*device or NULL*/, void* stream);
 int vmmt_normal_sample(const float* mu, const float* sd, const float* eps /*or NULL: Philox*/, float* z,

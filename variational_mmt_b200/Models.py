@@ -156,13 +156,17 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
         orig_tgt = tgt
         tgt = tgt[:-1]
         dec_gx = None
+        ops.stamp(0)                                             # (measurement aid: no-ops unless VMMT_STAMPS=1)
         if self.conditional:
             # target encoder over the transposed ids: recurrence along the batch axis (hazard H1).  It does not depend
-            # on the source encoder: the two stacks run side by side on two streams, each on its share of the SMs
+            # on the source encoder: the two stacks run side by side on two streams, each on its share of the SMs.  It is
+            # issued FIRST: its chain is the longer one (two input projections per layer, 40 steps), and with the source
+            # encoder issued first the target encoder finished 84 us later (measured with tools/phase_stamps.py)
             with ops.branch():
                 _, tgt_context = self.encoder_tgt(orig_tgt.transpose(0, 1), lengths=None)
-                tgt_context = tgt_context.transpose(0, 1)
+                tgt_context = ops.stamped(tgt_context, 2, 12).transpose(0, 1)
         enc_hidden, context = self.encoder(src, lengths)
+        context = ops.stamped(context, 1, 11)
         hook = getattr(self, "early_exchange_hook", None)
         if hook is not None and self.training and torch.is_grad_enabled():
             # data parallel (Optim.enable_early_exchange): the first encoder-stack backward node to run fires the early
@@ -203,6 +207,7 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             pz0.is_standard = True
         with ops.branch(lane=ops.LOW_LANE):                                      # p(v|z) beside the decoder: only the loss needs it
             p_v, _ = self.inf_net_image(z0_sample, context, lengths)
+        ops.stamp(3)                                             # latent block done on the main chain
         enc_state = self.decoder.init_decoder_state(src, context, enc_hidden)
         extra = {}
         if dec_gx is not None:
@@ -210,6 +215,7 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             extra["input_projection"] = dec_gx
         out, dec_state, attns = self.decoder(tgt, context, enc_state if dec_state is None else dec_state,
                                              lengths, image_features=None, z_sample=z0_sample, **extra)
+        out = ops.stamped(out, 4, 14)
         ops.join_branch(p_v.mean(), *([] if getattr(pz0, "is_standard", False) else pz0.params()), lane=ops.LOW_LANE)
         attns["p_global_image_features"] = [p_v]
         attns["ground_truth_global_image_features"] = [img_feats]

@@ -190,11 +190,14 @@ class NMTVIModel1LossCompute(nn.Module):
             state["output"] = state["output"][:shard_size]
             state["target"] = state["target"][:shard_size]
         loss, stats = self._compute_loss(batch, **state)
+        ops.stamp(5)
         hook = getattr(self, "before_backward", None)      # GraphedTrainStep: join the gradient memset issued beside the loss
         if hook is not None:
             hook()
             self.before_backward = None
         loss.div(normalization).backward()
+        ops.stamp(15)                   # backward's main chain done (measurement aid)
         ops.join_side()                 # weight-gradient GEMMs issued on the side stream are complete from here on
+        ops.stamp(16)
         batch_stats.update(stats)
         return batch_stats

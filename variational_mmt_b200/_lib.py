@@ -63,13 +63,14 @@ SIGNATURES = {
     "vmmt_lstm_cell_fwd": (I, [P, P, P, P, P, P, P, I, I, P]),
     "vmmt_attention_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "vmmt_attention_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P]),
-    "vmmt_masked_mean_fwd": (I, [P, P, P, L, I, I, I, P]),
-    "vmmt_masked_mean_bwd": (I, [P, L, P, P, I, I, I, I, P]),
+    "vmmt_masked_mean_fwd": (I, [P, L, L, P, P, L, I, I, I, P]),
+    "vmmt_masked_mean_bwd": (I, [P, L, P, P, L, L, I, I, I, I, P]),
     "vmmt_act_bwd": (I, [P, P, P, L, I, P]),
     "vmmt_loss_finalize": (I, [P, F, P, P]),
     "vmmt_colsum_acc": (I, [P, L, I, I, P, P, P]),
     "vmmt_axpy": (I, [P, P, F, L, P]),
     "vmmt_counter_add": (I, [P, U64, P]),
+    "vmmt_stamp": (I, [P, I, P]),
     "vmmt_dropout": (I, [P, P, L, F, U64, U64, P, P]),
     "vmmt_normal_sample": (I, [P, P, P, P, L, U64, U64, P, P]),
     "vmmt_kl_fwd": (I, [P, P, P, P, P, I, I, P]),

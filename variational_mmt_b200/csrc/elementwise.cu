@@ -27,25 +27,37 @@ __global__ void embedding_bwd_kernel(const int64_t* __restrict__ idx, const floa
 }
 
 // ---------------------------------------------------------------- masked mean (NormalVariationalEncoder.py:65-84)
-__global__ void masked_mean_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ len,
-                                       float* __restrict__ out, int64_t out_ld, int T, int B, int H) {
-  const int b = blockIdx.x;
+// x[t, b, k] at x + t * st + b * sb + k (time-major [T,B,H]: st = B*H, sb = H; the transposed view of a [B,T,H] tensor: st = H,
+// sb = T*H -- the target encoder's output needs no transposing copy).  One CTA per (b, 128 hidden units); the t-loop keeps
+// 8 independent loads in flight and adds them in t order (the sum is the same sequential fp32 sum for every launch shape).
+__global__ void __launch_bounds__(128)
+masked_mean_fwd_kernel(const float* __restrict__ x, int64_t st, int64_t sb, const int64_t* __restrict__ len,
+                       float* __restrict__ out, int64_t out_ld, int T, int H) {
+  const int b = blockIdx.x, k = blockIdx.y * 128 + threadIdx.x;
+  if (k >= H) return;
   const int L = min((int)len[b], T);
-  for (int k = threadIdx.x; k < H; k += blockDim.x) {
-    float s = 0.f;
-    for (int t = 0; t < L; ++t) s += x[((size_t)t * B + b) * H + k];
-    out[(size_t)b * out_ld + k] = s / (float)len[b];
+  const float* p = x + (size_t)b * sb + k;
+  float s = 0.f;
+  int t = 0;
+  for (; t + 8 <= L; t += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(t + u) * st);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
   }
+  for (; t < L; ++t) s += __ldg(p + (size_t)t * st);
+  out[(size_t)b * out_ld + k] = s / (float)len[b];
 }
 __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, int64_t dout_ld,
-                                       const int64_t* __restrict__ len, float* __restrict__ dx,
+                                       const int64_t* __restrict__ len, float* __restrict__ dx, int64_t st, int64_t sb,
                                        int T, int B, int H, int accumulate) {
   const int t = blockIdx.x / B, b = blockIdx.x % B;
   const bool on = t < (int)len[b];
   const float inv = 1.0f / (float)len[b];
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     const float g = on ? dout[(size_t)b * dout_ld + k] * inv : 0.f;
-    float* o = dx + ((size_t)t * B + b) * H + k;
+    float* o = dx + (size_t)t * st + (size_t)b * sb + k;
     *o = accumulate ? (*o + g) : g;
   }
 }
@@ -291,14 +303,17 @@ extern "C" int vmmt_embedding_bwd(const int64_t* idx, int64_t n, const float* do
   embedding_bwd_kernel<<<(unsigned)n, 128, 0, ST(stream)>>>(idx, dout, dtable, n, E, pad_idx);
   return vmmt_check_launch("embedding_bwd");
 }
-extern "C" int vmmt_masked_mean_fwd(const float* x, const int64_t* lengths, float* out,
+extern "C" int vmmt_masked_mean_fwd(const float* x, int64_t stride_t, int64_t stride_b, const int64_t* lengths, float* out,
                                     int64_t out_ld, int T, int B, int H, void* stream) {
-  masked_mean_fwd_kernel<<<B, 256, 0, ST(stream)>>>(x, lengths, out, out_ld, T, B, H);
+  if (B <= 0 || H <= 0) return VMMT_OK;
+  masked_mean_fwd_kernel<<<dim3(B, ceil_div(H, 128)), 128, 0, ST(stream)>>>(x, stride_t, stride_b, lengths, out, out_ld, T, H);
   return vmmt_check_launch("masked_mean_fwd");
 }
 extern "C" int vmmt_masked_mean_bwd(const float* dout, int64_t dout_ld, const int64_t* lengths,
-                                    float* dx, int accumulate, int T, int B, int H, void* stream) {
-  masked_mean_bwd_kernel<<<T * B, 128, 0, ST(stream)>>>(dout, dout_ld, lengths, dx, T, B, H, accumulate);
+                                    float* dx, int64_t stride_t, int64_t stride_b, int accumulate, int T, int B, int H,
+                                    void* stream) {
+  if (T <= 0 || B <= 0) return VMMT_OK;
+  masked_mean_bwd_kernel<<<T * B, 128, 0, ST(stream)>>>(dout, dout_ld, lengths, dx, stride_t, stride_b, T, B, H, accumulate);
   return vmmt_check_launch("masked_mean_bwd");
 }
 extern "C" int vmmt_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act,
@@ -340,6 +355,15 @@ extern "C" int vmmt_loss_finalize(float* stats8, float kl_weight, float* loss1, 
   return vmmt_check_launch("loss_finalize");
 }
 
+__global__ void stamp_kernel(unsigned long long* buf, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  buf[slot] = t;
+}
+extern "C" int vmmt_stamp(uint64_t* buf, int slot, void* stream) {
+  stamp_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<unsigned long long*>(buf), slot);
+  return vmmt_check_launch("stamp");
+}
 extern "C" int vmmt_counter_add(uint64_t* ctr, uint64_t inc, void* stream) {
   counter_add_kernel<<<1, 1, 0, ST(stream)>>>(ctr, inc);
   return vmmt_check_launch("counter_add");

@@ -13,6 +13,8 @@ What makes replays differ from each other although every kernel argument is bake
 the Philox offsets of dropout / latent noise are taken relative to a device-resident counter
 (``ops.rng_base``) that a one-thread kernel at the end of the graph advances.
 """
+import os
+
 import torch
 
 from . import ops
@@ -117,17 +119,20 @@ class GraphedTrainStep(object):
             if self.optim is not None:
                 self.optim._early_done = early_done
         torch.cuda.current_stream(self.device).wait_stream(side)
-        g = torch.cuda.CUDAGraph()
+        dot = os.environ.get("VMMT_GRAPH_DOT")              # debug: dump the captured step as DOT (cudaGraphDebugDotPrint)
+        g = torch.cuda.CUDAGraph(keep_graph=True) if dot else torch.cuda.CUDAGraph()
         l0 = _lib.lib.vmmt_launch_count()
         # captured on a HIGH-priority stream (as are the branch / loss streams): kernel-node priorities are recorded, so
         # the critical chain's CTAs are placed before those of the weight-gradient lanes (default = lowest priority)
         if self._capture_stream is None:
-            import os
             self._capture_stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("VMMT_MAIN_PRIO", "-1")))
         with torch.cuda.graph(g, pool=self._pool, stream=self._capture_stream):
             ops.begin_step()
             vec = self._run(*static, normalization)
             ops.advance_rng()
+        if dot:
+            g.debug_dump(dot)
+            g.instantiate()
         self.kernels_per_replay = int(_lib.lib.vmmt_launch_count() - l0)
         if self._pool is None:
             self._pool = g.pool()

@@ -260,10 +260,21 @@ def _fire_early_exchange(after_event=None):
         fn(after_event)
 
 
+_gx = {}
+
+
+def _gx_stream(device):
+    """Second stream for the reverse direction's input projection of a bidirectional layer (same priority as the chain)."""
+    st = _gx.get(device)
+    if st is None:
+        st = _gx[device] = torch.cuda.Stream(device=device, priority=int(os.environ.get("VMMT_BRANCH_PRIO", "-1")))
+    return st
+
+
 def aux_streams():
     """Every helper stream this module has created (side lanes, branch lanes, loss stream): what a consumer of ALL the
     gradients issued so far has to wait for."""
-    out = list(_side["streams"]) + list(_branch["streams"].values())
+    out = list(_side["streams"]) + list(_branch["streams"].values()) + list(_gx.values())
     if _loss_stream is not None:
         out.append(_loss_stream)
     return out
@@ -631,9 +642,18 @@ class LSTMLayerFn(Function):
             rowbias = rowbias.contiguous()
         dirs = (L.LstmDir * ndir)()
         x2 = x.view(T * N, In)
+        # input projections: the reverse direction's GEMM runs beside the forward direction's on a second stream (each is
+        # ~80 tiles: together they fill the SMs; back to back they were 2 x 22 us at the head of the target-encoder chain)
+        fork = None
+        if ndir == 2 and not gx_given and x.is_cuda and _branch["enabled"]:
+            cur = torch.cuda.current_stream(dev)
+            fork = _gx_stream(dev)
+            fork.wait_stream(cur)
+            with torch.cuda.stream(fork):
+                gemm(x2, weights[4][:, c0c:c1c], gx[1].view(T * N, 4 * Hd), T * N, 4 * Hd, In)
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d: 4 * d + 4]
-            if not gx_given:
+            if not gx_given and not (d == 1 and fork is not None):
                 gemm(x2, w_ih[:, c0c:c1c], gx[d].view(T * N, 4 * Hd), T * N, 4 * Hd, In)
             D = dirs[d]
             D.gx, D.w_hh, D.b_ih, D.b_hh = fptr(gx[d]), fptr(w_hh), fptr(b_ih), fptr(b_hh)
@@ -646,6 +666,8 @@ class LSTMLayerFn(Function):
             D.gates = fptr(gates[d]) if save else None
             D.cs = fptr(cs[d]) if save else None
             D.reverse = 1 if d == 1 else 0
+        if fork is not None:
+            torch.cuda.current_stream(dev).wait_stream(fork)
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
         L.call("vmmt_lstm_seq_fwd", dirs, ndir, ptr(lengths), T, N, Hd, flags(), int(cfg.get("cluster_budget") or 0),
@@ -793,26 +815,79 @@ class AttentionCoreFn(Function):
 
 
 class MaskedMeanFn(Function):
-    """GlobalInferenceNetwork.encode_seq (onmt/modules/NormalVariationalEncoder.py:65-84)."""
+    """GlobalInferenceNetwork.encode_seq (onmt/modules/NormalVariationalEncoder.py:65-84).  ``x`` may be time-major
+    contiguous or the transposed view of a contiguous [B,T,H] tensor (the target encoder's output): the kernels take the
+    two strides, and the gradient comes back in the layout of the input, so neither direction needs a transposing copy."""
+
+    @staticmethod
+    def _layout(x):
+        T, B, H = x.shape
+        if x.stride(2) == 1 and x.stride(0) == H and x.stride(1) == T * H and T > 1 and B > 1:
+            return "bt"                                   # transposed view of [B,T,H]
+        return "tb"
 
     @staticmethod
     def forward(ctx, x, lengths):
-        x = x.contiguous()
+        lay = MaskedMeanFn._layout(x)
+        if lay == "tb":
+            x = x.contiguous()
         T, B, H = x.shape
+        st, sb = (B * H, H) if lay == "tb" else (H, T * H)
         out = torch.empty(B, H, device=x.device, dtype=torch.float32)
-        L.call("vmmt_masked_mean_fwd", fptr(x), ptr(lengths), fptr(out), H, T, B, H, stream())
+        L.call("vmmt_masked_mean_fwd", fptr(x), st, sb, ptr(lengths), fptr(out), H, T, B, H, stream())
         ctx.save_for_backward(lengths)
-        ctx.dims = (T, B, H)
+        ctx.dims = (T, B, H, lay)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (lengths,) = ctx.saved_tensors
-        T, B, H = ctx.dims
+        T, B, H, lay = ctx.dims
         dout = dout.contiguous()
-        dx = torch.empty(T, B, H, device=dout.device, dtype=torch.float32)
-        L.call("vmmt_masked_mean_bwd", fptr(dout), H, ptr(lengths), fptr(dx), 0, T, B, H, stream())
+        if lay == "tb":
+            dx = torch.empty(T, B, H, device=dout.device, dtype=torch.float32)
+            st, sb = B * H, H
+        else:
+            base = torch.empty(B, T, H, device=dout.device, dtype=torch.float32)
+            dx = base.transpose(0, 1)
+            st, sb = H, T * H
+        L.call("vmmt_masked_mean_bwd", fptr(dout), H, ptr(lengths), dx.data_ptr(), st, sb, 0, T, B, H, stream())
         return dx, None
+
+
+# ---- phase stamps (measurement aid, VMMT_STAMPS=1): %globaltimer written by one-thread kernels at chosen points of the
+# forward pass and, through StampFn's backward, of the backward pass -- phase boundaries of a replayed step with no profiler
+# attached (tools/phase_stamps.py)
+_stamps = {"on": os.environ.get("VMMT_STAMPS") == "1", "buf": None}
+
+
+def stamp_buffer():
+    if _stamps["buf"] is None:
+        _stamps["buf"] = torch.zeros(64, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+    return _stamps["buf"]
+
+
+def stamp(slot):
+    if _stamps["on"]:
+        L.call("vmmt_stamp", stamp_buffer().data_ptr(), int(slot), stream())
+
+
+class StampFn(Function):
+    @staticmethod
+    def forward(ctx, x, slot_fwd, slot_bwd):
+        stamp(slot_fwd)
+        ctx.slot_bwd = slot_bwd
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        stamp(ctx.slot_bwd)
+        return g, None, None
+
+
+def stamped(x, slot_fwd, slot_bwd):
+    """Identity; records when ``x`` is ready (forward) and when its gradient is ready (backward)."""
+    return StampFn.apply(x, slot_fwd, slot_bwd) if (_stamps["on"] and x.requires_grad) else x
 
 
 _dropout_log = [None]
