@@ -146,6 +146,8 @@ class NMTVIModel(FlatParamsMixin, nn.Module):
             self.encoder_tgt.rnn.fires_early_exchange = True
             self.encoder.rnn.cluster_budget = int(os.environ.get("VMMT_ENC_BUDGET", "5")) or None
             self.encoder_tgt.rnn.cluster_budget = int(os.environ.get("VMMT_TGT_BUDGET", "8")) or None
+            self.encoder.rnn.cluster_budget_bwd = int(os.environ.get("VMMT_ENC_BUDGET_BWD", "0")) or None
+            self.encoder_tgt.rnn.cluster_budget_bwd = int(os.environ.get("VMMT_TGT_BUDGET_BWD", "0")) or None
         self.inf_net_global = kwargs["inf_net_global"]
         self.gen_net_global = kwargs["gen_net_global"]
         self.inf_net_image = kwargs["inf_net_image"]

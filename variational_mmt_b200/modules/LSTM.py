@@ -55,6 +55,7 @@ class LSTM(nn.Module):
             c0 = hx[1][l * ndir:(l + 1) * ndir] if hx is not None else None
             cfg = {"save": save, "in_cols": in_cols if l == 0 else None, "gx_given": gx_given and l == 0,
                    "cluster_budget": self.cluster_budget if self.training else None,
+                   "cluster_budget_bwd": getattr(self, "cluster_budget_bwd", None) if self.training else None,
                    # weight gradients of a bidirectional stack (the target encoder: lanes 2 + direction) and of a
                    # unidirectional one (source encoder / decoder: lane = layer parity) go to different side streams: the
                    # two encoders' backward passes run concurrently and their last weight-gradient blocks are the tail of

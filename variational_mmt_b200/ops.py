@@ -676,7 +676,7 @@ class LSTMLayerFn(Function):
             ctx.save_for_backward(None if gx_given else x, out, gates, cs, h0, c0, rowbias, lengths)
             ctx.weights, ctx.cfg = weights, (ndir, T, N, In, Hd, c0c, c1c)
             ctx.gx_given = gx_given
-            ctx.cluster_budget = int(cfg.get("cluster_budget") or 0)
+            ctx.cluster_budget = int(cfg.get("cluster_budget_bwd") or cfg.get("cluster_budget") or 0)
             ctx.side_lane = cfg.get("side_lane")
             ctx.fires_early_exchange = bool(cfg.get("fires_early_exchange"))
         ctx.set_materialize_grads(False)
