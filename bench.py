@@ -548,7 +548,7 @@ def run_decode(args):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.call("vmmt_generator_topk", fptr(x), fptr(gen.weight), fptr(gen.bias), R_, H, V, 5, fptr(ws), wsb, stream())
+            _lib.call("vmmt_generator_topk", fptr(x), fptr(gen.weight), fptr(gen.bias), R_, H, V, 5, fptr(ws), wsb, ops.flags(), stream())
             e1.record()
             torch.cuda.synchronize()
             if it >= 3:

@@ -1,6 +1,6 @@
 """Small-shape driver for compute-sanitizer (memcheck / racecheck / synccheck): the cluster LSTM recurrence forward and
 BPTT (mbarrier + st.async / bulk-copy DSMEM hand-off, tcgen05), the row-MLP kernel (cluster split-K through DSMEM), the
-tcgen05 GEMM (TMA + TMEM) and the peer barrier / exchange kernels at world 1.
+tcgen05 GEMM (TMA + TMEM), the attention v2 kernels (cp.async staging) and the peer barrier / exchange kernels at world 1.
     compute-sanitizer --tool racecheck python tools/sanitize_target.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,7 @@ import variational_mmt_b200 as vm
 from variational_mmt_b200 import ops
 dev = "cuda"
 torch.manual_seed(0)
-what = sys.argv[1:] or ["lstm", "rowmlp", "gemm", "peer"]
+what = sys.argv[1:] or ["lstm", "rowmlp", "gemm", "attention", "peer"]
 if "lstm" in what:
     for (T, N, In, H, ndir, masked) in [(4, 5, 32, 64, 1, True), (3, 12, 32, 96, 2, False)]:
         x = (torch.randn(T, N, In, device=dev) * 0.5).requires_grad_(True)
@@ -39,6 +39,22 @@ if "gemm" in what:
     ops.gemm(a, b, c, 130, 96, 200, bias=torch.randn(96, device=dev), act=2)
     torch.cuda.synchronize()
     print("gemm ok", float(c.norm()))
+if "attention" in what:
+    # v2 kernels (cp.async staging, K split over warps): resident-context path, two source blocks, v1 fallback (H % 4 != 0),
+    # and the strided masked mean
+    for (T, B, S, H) in [(19, 3, 11, 64), (17, 2, 50, 96), (5, 2, 33, 30)]:
+        qp = (torch.randn(T, B, H, device=dev) * 0.3).requires_grad_(True)
+        cx = (torch.randn(S, B, H, device=dev) * 0.3).requires_grad_(True)
+        ln = torch.tensor([S] + [max(1, S - 3 * i) for i in range(1, B)], device=dev)
+        cv, al = ops.AttentionCoreFn.apply(qp, cx, ln)
+        (cv * torch.randn_like(cv)).sum().backward()
+        torch.cuda.synchronize()
+        print("attention T=%d B=%d S=%d H=%d ok %.4f" % (T, B, S, H, float(cv.norm())))
+    y = torch.randn(6, 9, 40, device=dev, requires_grad=True)
+    m = ops.MaskedMeanFn.apply(y.transpose(0, 1), torch.tensor([9, 7, 7, 3, 2, 1], device=dev))
+    m.sum().backward()
+    torch.cuda.synchronize()
+    print("masked mean (transposed view) ok %.4f" % float(m.norm()))
 if "peer" in what:
     from variational_mmt_b200.flat import FlatParamsMixin
 
