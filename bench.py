@@ -362,6 +362,33 @@ def run_ours(args):
                              "kind": "oracle port on cuda (torch eager: cuDNN LSTM + cuBLAS)", "sample": r["sample"]}
             except Exception as e:                        # noqa: BLE001
                 gpu_torch = {"error": "%s: %s" % (type(e).__name__, e)}
+        bf16_line = None
+        if n_gpus == 1 and args.dtype == "f32" and not args.no_decode and graphed is not None:
+            # the bf16-operand variant of the same step (BASELINE configs[1] "fp32 and bf16"; tolerance stated in
+            # tests/test_gpu_parity.py::BF16_TOL): same model / optimiser / batches, its own captured graph
+            try:
+                ops.set_gemm_mode(2)
+                g16 = vm.GraphedTrainStep(model, loss_fn, shard_size=shard, optim=optim)
+                for i in range(5):
+                    g16(*resident[i % NB], norm); optim.step()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                nb16, tok16 = min(args.steps, 30), 0
+                e0.record()
+                for i in range(nb16):
+                    g16(*resident[i % NB], norm); optim.step()
+                    tok16 += tokens[i % NB]
+                e1.record()
+                torch.cuda.synchronize()
+                ms16 = e0.elapsed_time(e1)
+                bf16_line = {"value": tok16 / (ms16 / 1e3), "unit": "tokens/s", "ms_per_step": ms16 / nb16, "steps": nb16,
+                             "dtype": "bf16 operands in the forward GEMMs and the generator (fp32 accumulate / state / master "
+                                      "weights); full line: bench.py --dtype bf16"}
+                del g16
+            except Exception as e:                        # noqa: BLE001
+                bf16_line = {"error": "%s: %s" % (type(e).__name__, e)}
+            finally:
+                ops.set_gemm_mode(0)
         decode_line = None
         if n_gpus == 1 and args.workload == "cfg1" and not args.no_decode:
             try:
@@ -413,6 +440,7 @@ def run_ours(args):
             "cpu_baseline": cpu_b,
             "gpu_torch_baseline": gpu_torch,
             "decode": decode_line,
+            "bf16_variant": bf16_line,
             "dp_parity": dp_parity,
             "top_calls_ms": {k: round(v[1], 3) for k, v in top[:8]},
             "roofline_others": others,
