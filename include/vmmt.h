@@ -68,9 +68,10 @@ int vmmt_gemm_bf16(const void* A, int64_t lda, int a_kmajor, const void* B, int6
                    int M, int N, int K, const float* bias, int act, int accumulate, int flags, void* stream);
 
 /* Embedding gather / dense scatter-add (Embeddings.py:169-188; nn.Embedding padding_idx row gets no grad). */
-int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int E, float* out, void* stream);
+/* `rows` = rows of the table: an index outside [0, rows) traps on the device (nn.Embedding / numpy fancy indexing raise) */
+int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int64_t rows, int E, float* out, void* stream);
 int vmmt_embedding_bwd(const int64_t* idx, int64_t n, const float* dout, int E, int64_t pad_idx,
-                       float* dtable, void* stream);
+                       float* dtable, int64_t rows, void* stream);
 
 /* ---- LSTM recurrence, one layer, one or two directions per launch (nn.LSTM: Models.py:124-149,
  * 892-893; VI_Model1.py:106).  gx = x W_ih^T (no bias) is computed by vmmt_gemm beforehand. */

@@ -54,8 +54,8 @@ SIGNATURES = {
     "vmmt_gemm_dual": (I, [P, L, P, L, I, P, L, P, L, I, P, L, I, I, P, I, I, P]),
     "vmmt_cast_bf16": (I, [P, L, P, L, I, I, P]),
     "vmmt_gemm_bf16": (I, [P, L, I, P, L, I, P, L, I, I, I, P, I, I, I, P]),
-    "vmmt_embedding_fwd": (I, [P, L, P, I, P, P]),
-    "vmmt_embedding_bwd": (I, [P, L, P, I, L, P, P]),
+    "vmmt_embedding_fwd": (I, [P, L, P, L, I, P, P]),
+    "vmmt_embedding_bwd": (I, [P, L, P, I, L, P, L, P]),
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_lstm_seq_supported": (I, [I, I, I]),
     "vmmt_lstm_seq_fwd": (I, [C.POINTER(LstmDir), I, P, I, I, I, I, I, P, SZ, P]),

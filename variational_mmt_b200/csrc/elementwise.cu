@@ -2,6 +2,7 @@
 // activation derivatives, bias-gradient column sums, Philox dropout, the latent block
 // (sample + analytic KL) and the image-feature head's gate and loss.
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include "common.cuh"
 #include "vmmt_internal.h"
 
@@ -9,18 +10,27 @@ namespace {
 
 // ---------------------------------------------------------------- embeddings (Embeddings.py:169-188)
 __global__ void embedding_fwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ table,
-                                     float* __restrict__ out, int64_t n, int E) {
+                                     float* __restrict__ out, int64_t n, int E, int64_t rows) {
   const int64_t row = blockIdx.x;
-  const float* src = table + idx[row] * (int64_t)E;
+  const int64_t id = idx[row];
+  if (id < 0 || id >= rows) {                        // nn.Embedding / numpy fancy indexing raise; here: a device-side trap
+    if (threadIdx.x == 0) printf("vmmt_embedding_fwd: index %lld out of range [0, %lld) at position %lld\n", (long long)id, (long long)rows, (long long)row);
+    __trap();
+  }
+  const float* src = table + id * (int64_t)E;
   float* dst = out + row * E;
   for (int k = threadIdx.x; k < E; k += blockDim.x) dst[k] = src[k];
 }
 // dense scatter-add; the padding row receives no gradient (nn.Embedding padding_idx)
 __global__ void embedding_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dout,
-                                     float* __restrict__ dtable, int64_t n, int E, int64_t pad) {
+                                     float* __restrict__ dtable, int64_t n, int E, int64_t pad, int64_t rows) {
   const int64_t row = blockIdx.x;
   const int64_t id = idx[row];
   if (id == pad) return;
+  if (id < 0 || id >= rows) {
+    if (threadIdx.x == 0) printf("vmmt_embedding_bwd: index %lld out of range [0, %lld) at position %lld\n", (long long)id, (long long)rows, (long long)row);
+    __trap();
+  }
   const float* src = dout + row * E;
   float* dst = dtable + id * (int64_t)E;
   for (int k = threadIdx.x; k < E; k += blockDim.x) atomicAdd(dst + k, src[k]);
@@ -291,16 +301,16 @@ __global__ void image_loss_bwd_kernel(const float* __restrict__ loc, const float
 
 #define ST(s) ((cudaStream_t)(s))
 
-extern "C" int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int E,
+extern "C" int vmmt_embedding_fwd(const int64_t* idx, int64_t n, const float* table, int64_t rows, int E,
                                   float* out, void* stream) {
   if (n <= 0) return VMMT_OK;
-  embedding_fwd_kernel<<<(unsigned)n, 128, 0, ST(stream)>>>(idx, table, out, n, E);
+  embedding_fwd_kernel<<<(unsigned)n, 128, 0, ST(stream)>>>(idx, table, out, n, E, rows);
   return vmmt_check_launch("embedding_fwd");
 }
 extern "C" int vmmt_embedding_bwd(const int64_t* idx, int64_t n, const float* dout, int E,
-                                  int64_t pad_idx, float* dtable, void* stream) {
+                                  int64_t pad_idx, float* dtable, int64_t rows, void* stream) {
   if (n <= 0) return VMMT_OK;
-  embedding_bwd_kernel<<<(unsigned)n, 128, 0, ST(stream)>>>(idx, dout, dtable, n, E, pad_idx);
+  embedding_bwd_kernel<<<(unsigned)n, 128, 0, ST(stream)>>>(idx, dout, dtable, n, E, pad_idx, rows);
   return vmmt_check_launch("embedding_bwd");
 }
 extern "C" int vmmt_masked_mean_fwd(const float* x, int64_t stride_t, int64_t stride_b, const int64_t* lengths, float* out,

@@ -194,7 +194,7 @@ class ImageFeatureTable(object):
         B = idx.numel()
         if out is None:
             out = torch.empty(B, self.dim, device=self.device, dtype=torch.float32)
-        L.call("vmmt_embedding_fwd", ptr(idx), B, fptr(self.table), self.dim, fptr(out), stream())
+        L.call("vmmt_embedding_fwd", ptr(idx), B, fptr(self.table), self.table.shape[0], self.dim, fptr(out), stream())
         return out
 
     __call__ = gather

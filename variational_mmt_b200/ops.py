@@ -362,7 +362,7 @@ class EmbeddingFn(Function):
         idx = idx.contiguous()
         n, E = idx.numel(), weight.shape[1]
         out = torch.empty(*idx.shape, E, device=weight.device, dtype=torch.float32)
-        L.call("vmmt_embedding_fwd", ptr(idx), n, fptr(weight), E, fptr(out), stream())
+        L.call("vmmt_embedding_fwd", ptr(idx), n, fptr(weight), weight.shape[0], E, fptr(out), stream())
         ctx.save_for_backward(idx)
         ctx.weight, ctx.pad_idx = weight, pad_idx
         return out
@@ -373,7 +373,7 @@ class EmbeddingFn(Function):
         w = ctx.weight
         dout = dout.contiguous()
         L.call("vmmt_embedding_bwd", ptr(idx), idx.numel(), fptr(dout), w.shape[1], ctx.pad_idx,
-               fptr(grad_buf(w)), stream())
+               fptr(grad_buf(w)), w.shape[0], stream())
         return None, None, None, None
 
 

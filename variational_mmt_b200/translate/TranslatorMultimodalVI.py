@@ -132,7 +132,8 @@ class TranslatorMultimodalVI(object):
         w, gen = dec.rnn, model.generator[0]
         V = gen.weight.size(0)
         sm = stream()
-        L.call("vmmt_embedding_fwd", ptr(st.tok_cur), R, fptr(dec.embeddings.word_lut.weight), E, fptr(st.emb), sm)
+        L.call("vmmt_embedding_fwd", ptr(st.tok_cur), R, fptr(dec.embeddings.word_lut.weight),
+               dec.embeddings.word_lut.weight.shape[0], E, fptr(st.emb), sm)
         x = st.emb
         for l in range(nl):
             w_ih, w_hh = getattr(w, "weight_ih_l%d" % l), getattr(w, "weight_hh_l%d" % l)
