@@ -105,6 +105,8 @@ typedef struct VmmtLstmDirBwd {
   float* dgates;         /* [T,N,4H] OUT: gradient wrt the pre-activation gates (= d gx) */
   float* dh0;            /* [N,H] OUT or NULL */
   float* dc0;
+  float* db_ih;          /* [4H] or NULL: bias gradient sum_{t,n} dgates ACCUMULATED (+=) by the launch -- only when */
+  float* db_hh;          /* vmmt_lstm_seq_bwd_fuses_bias() says so (else ignored: use vmmt_colsum_acc on dgates) */
   int32_t reverse;
   int32_t pad_;
 } VmmtLstmDirBwd;
@@ -115,6 +117,8 @@ int vmmt_lstm_seq_supported(int ndir, int N, int H);
  * independent recurrences issued on two streams (source encoder / target encoder) share the GPU with it. */
 int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int flags,
                       int cluster_budget, void* workspace, size_t workspace_bytes, void* stream);
+/* 1 when vmmt_lstm_seq_bwd with these arguments accumulates db_ih / db_hh itself (the tensor-core cluster recurrence) */
+int vmmt_lstm_seq_bwd_fuses_bias(int ndir, int N, int H, int flags);
 int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths, int T, int N, int H, int flags,
                       int cluster_budget, void* workspace, size_t workspace_bytes, void* stream);
 /* single-step cell on pre-summed gate pre-activations (decode with large sentences x beam). */

@@ -31,7 +31,7 @@ class LstmDir(C.Structure):
 
 class LstmDirBwd(C.Structure):
     _fields_ = [("w_hh", P), ("gates", P), ("cs", P), ("c0", P), ("dout", P), ("dout_ld", L),
-                ("dhT", P), ("dcT", P), ("dgates", P), ("dh0", P), ("dc0", P),
+                ("dhT", P), ("dcT", P), ("dgates", P), ("dh0", P), ("dc0", P), ("db_ih", P), ("db_hh", P),
                 ("reverse", C.c_int32), ("pad_", C.c_int32)]
 
 
@@ -59,6 +59,7 @@ SIGNATURES = {
     "vmmt_lstm_workspace_bytes": (SZ, [I, I, I]),
     "vmmt_lstm_seq_supported": (I, [I, I, I]),
     "vmmt_lstm_seq_fwd": (I, [C.POINTER(LstmDir), I, P, I, I, I, I, I, P, SZ, P]),
+    "vmmt_lstm_seq_bwd_fuses_bias": (I, [I, I, I, I]),
     "vmmt_lstm_seq_bwd": (I, [C.POINTER(LstmDirBwd), I, P, I, I, I, I, I, P, SZ, P]),
     "vmmt_lstm_cell_fwd": (I, [P, P, P, P, P, P, P, I, I, P]),
     "vmmt_attention_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),

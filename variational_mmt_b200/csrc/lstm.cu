@@ -447,12 +447,20 @@ extern "C" int vmmt_lstm_seq_fwd(const VmmtLstmDir* dirs, int ndir, const int64_
   return resident_launch(lstm_fwd_kernel, ndir * p.G * p.C, p.smem, &P, s, "lstm_fwd_kernel");
 }
 
+static bool bwd_takes_tc_path(int ndir, int N, int H, int flags) {
+  return !(flags & VMMT_F_EXACT) && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_SIMT_BWD") &&
+         !getenv("VMMT_LSTM_STEPWISE") && vmmt_lstm_tc_supported(ndir, N, H);
+}
+
+extern "C" int vmmt_lstm_seq_bwd_fuses_bias(int ndir, int N, int H, int flags) {
+  return (bwd_takes_tc_path(ndir, N, H, flags) && !getenv("VMMT_LSTM_NO_BIAS_FUSE")) ? 1 : 0;
+}
+
 extern "C" int vmmt_lstm_seq_bwd(const VmmtLstmDirBwd* dirs, int ndir, const int64_t* lengths,
                                  int T, int N, int H, int flags, int cluster_budget, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   VMMT_REQUIRE(ndir == 1 || ndir == 2, "lstm_seq_bwd: ndir must be 1 or 2 (got %d)", ndir);
-  if (!(flags & VMMT_F_EXACT) && !getenv("VMMT_LSTM_SIMT") && !getenv("VMMT_LSTM_SIMT_BWD") &&
-      !getenv("VMMT_LSTM_STEPWISE") && vmmt_lstm_tc_supported(ndir, N, H))
+  if (bwd_takes_tc_path(ndir, N, H, flags))
     return vmmt_lstm_tc_bwd(dirs, ndir, lengths, T, N, H, cluster_budget, (cudaStream_t)stream);
   if (workspace_bytes < vmmt_lstm_workspace_bytes(ndir, N, H)) {
     vmmt_set_error("lstm_seq_bwd: workspace too small");

@@ -717,6 +717,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   };
   if (warp < EW) { load_raw(0); derive(); }
   const int q = warp & 3, hf = warp >> 2;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};                      // bias gradient of this thread's unit: sum of dG over its rows and t
 
   for (int s = 0; s < T; ++s) {
     const int t = D.reverse ? s : T - 1 - s;
@@ -740,6 +741,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
           dGs[r][3] = m ? dh * pf[r][4] : 0.f;
           dc[r] = m ? dct * pf[r][5] : dc[r];
           dhr[r] = m ? 0.f : dhr[r];                        // consumed (the next value comes from the reduce below) / frozen: passes through
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bsum[g] += dGs[r][g];
           // operand tile: k = gate*32 + lane (this CTA's 128 gate rows), row n (hi) and NPc + n (lo)
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -862,6 +865,24 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
         if (D.dh0) D.dh0[(size_t)(n0 + n) * H + unit] = dhr[r];
         if (D.dc0) D.dc0[(size_t)(n0 + n) * H + unit] = dc[r];
       }
+    }
+  }
+  // bias gradients db_ih = db_hh = sum over (t, n) of dG: the 8 cell-owner warps hold per-unit partial sums over their rows;
+  // they are added in warp order through shared memory (the receive buffer is idle: the last hand-off has been consumed)
+  // and one atomicAdd per (gate, unit) joins the batch groups' shares (replaces a column-sum pass over the 10 MB dG tensor)
+  if (D.db_ih != nullptr || D.db_hh != nullptr) {
+    __syncthreads();
+    if (warp < EW) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) recv[(warp * 4 + g) * 32 + lane] = bsum[g];
+    }
+    __syncthreads();
+    if (warp < 4 && u0 + lane < H) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < EW; ++w) tot += recv[(w * 4 + warp) * 32 + lane];
+      if (D.db_ih) atomicAdd(D.db_ih + (size_t)warp * H + u0 + lane, tot);
+      if (D.db_hh) atomicAdd(D.db_hh + (size_t)warp * H + u0 + lane, tot);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -701,6 +701,7 @@ class LSTMLayerFn(Function):
         dh0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
         dc0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
         dirs = (L.LstmDirBwd * ndir)()
+        fused_bias = bool(L.lib.vmmt_lstm_seq_bwd_fuses_bias(ndir, N, Hd, flags()))
         for d in range(ndir):
             D = dirs[d]
             D.w_hh, D.gates, D.cs = fptr(weights[4 * d + 1]), fptr(gates[d]), fptr(cs[d])
@@ -712,6 +713,10 @@ class LSTMLayerFn(Function):
             D.dgates = fptr(dg[d])
             D.dh0 = fptr(dh0[d]) if need_h0 else None
             D.dc0 = fptr(dc0[d]) if need_h0 else None
+            if fused_bias:                                # the recurrence kernel adds sum_{t,n} dG into the bias gradients
+                b_ih, b_hh = weights[4 * d + 2], weights[4 * d + 3]
+                D.db_ih = fptr(grad_buf(b_ih)) if b_ih.requires_grad else None
+                D.db_hh = fptr(grad_buf(b_hh)) if b_hh.requires_grad else None
             D.reverse = 1 if d == 1 else 0
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
@@ -762,7 +767,9 @@ class LSTMLayerFn(Function):
                     t0 = 0 if d == 0 else T - 1
                     gemm(dg[d][t0], h0[d], grad_buf(w_hh), 4 * Hd, Hd, N, a_kmajor=False, b_kmajor=False,
                          accumulate=1)
-                if b_ih.requires_grad and b_hh.requires_grad:              # identical sums: one pass, two outputs
+                if fused_bias:
+                    pass                                                   # done inside the recurrence kernel
+                elif b_ih.requires_grad and b_hh.requires_grad:            # identical sums: one pass, two outputs
                     colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih), grad_buf(b_hh))
                 elif b_ih.requires_grad or b_hh.requires_grad:
                     colsum_acc(dg2, T * N, 4 * Hd, grad_buf(b_ih if b_ih.requires_grad else b_hh))
