@@ -107,6 +107,7 @@ typedef struct VmmtLstmDirBwd {
   float* dc0;
   float* db_ih;          /* [4H] or NULL: bias gradient sum_{t,n} dgates ACCUMULATED (+=) by the launch -- only when */
   float* db_hh;          /* vmmt_lstm_seq_bwd_fuses_bias() says so (else ignored: use vmmt_colsum_acc on dgates) */
+  float* drow;           /* [N,4H] or NULL: gradient of `rowbias` = sum_t dgates, WRITTEN under the same condition */
   int32_t reverse;
   int32_t pad_;
 } VmmtLstmDirBwd;

@@ -31,7 +31,7 @@ class LstmDir(C.Structure):
 
 class LstmDirBwd(C.Structure):
     _fields_ = [("w_hh", P), ("gates", P), ("cs", P), ("c0", P), ("dout", P), ("dout_ld", L),
-                ("dhT", P), ("dcT", P), ("dgates", P), ("dh0", P), ("dc0", P), ("db_ih", P), ("db_hh", P),
+                ("dhT", P), ("dcT", P), ("dgates", P), ("dh0", P), ("dc0", P), ("db_ih", P), ("db_hh", P), ("drow", P),
                 ("reverse", C.c_int32), ("pad_", C.c_int32)]
 
 

@@ -718,6 +718,11 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
   if (warp < EW) { load_raw(0); derive(); }
   const int q = warp & 3, hf = warp >> 2;
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};                      // bias gradient of this thread's unit: sum of dG over its rows and t
+  float rsum[RM][4];                                         // per-row sums over t: gradient of the per-example additive term
+#pragma unroll
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rsum[r][g] = 0.f;
 
   for (int s = 0; s < T; ++s) {
     const int t = D.reverse ? s : T - 1 - s;
@@ -742,7 +747,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
           dc[r] = m ? dct * pf[r][5] : dc[r];
           dhr[r] = m ? 0.f : dhr[r];                        // consumed (the next value comes from the reduce below) / frozen: passes through
 #pragma unroll
-          for (int g = 0; g < 4; ++g) bsum[g] += dGs[r][g];
+          for (int g = 0; g < 4; ++g) { bsum[g] += dGs[r][g]; rsum[r][g] += dGs[r][g]; }
           // operand tile: k = gate*32 + lane (this CTA's 128 gate rows), row n (hi) and NPc + n (lo)
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -864,6 +869,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_tc_bwd_kernel(const TcBwdPara
       if (ulive && r < nr) {
         if (D.dh0) D.dh0[(size_t)(n0 + n) * H + unit] = dhr[r];
         if (D.dc0) D.dc0[(size_t)(n0 + n) * H + unit] = dc[r];
+        if (D.drow) {                                       // d(rowbias)[n, gate, unit] = sum_t dG: one owner per element
+          float* dr = D.drow + (size_t)(n0 + n) * 4 * H + unit;
+          dr[0] = rsum[r][0]; dr[(size_t)H] = rsum[r][1]; dr[(size_t)2 * H] = rsum[r][2]; dr[(size_t)3 * H] = rsum[r][3];
+        }
       }
     }
   }

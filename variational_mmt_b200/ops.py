@@ -702,6 +702,9 @@ class LSTMLayerFn(Function):
         dc0 = torch.empty(ndir, N, Hd, device=dev, dtype=torch.float32) if need_h0 else None
         dirs = (L.LstmDirBwd * ndir)()
         fused_bias = bool(L.lib.vmmt_lstm_seq_bwd_fuses_bias(ndir, N, Hd, flags()))
+        need_drow = rowbias is not None and ctx.needs_input_grad[4]
+        # (the per-example term enters every direction: only the one-direction case is summed inside the kernel)
+        drow = torch.empty(N, 4 * Hd, device=dev, dtype=torch.float32) if (need_drow and fused_bias and ndir == 1) else None
         for d in range(ndir):
             D = dirs[d]
             D.w_hh, D.gates, D.cs = fptr(weights[4 * d + 1]), fptr(gates[d]), fptr(cs[d])
@@ -717,6 +720,7 @@ class LSTMLayerFn(Function):
                 b_ih, b_hh = weights[4 * d + 2], weights[4 * d + 3]
                 D.db_ih = fptr(grad_buf(b_ih)) if b_ih.requires_grad else None
                 D.db_hh = fptr(grad_buf(b_hh)) if b_hh.requires_grad else None
+                D.drow = fptr(drow) if drow is not None else None
             D.reverse = 1 if d == 1 else 0
         ws_bytes = L.lib.vmmt_lstm_workspace_bytes(ndir, N, Hd)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
@@ -727,14 +731,13 @@ class LSTMLayerFn(Function):
         x2 = x.view(T * N, In) if not gx_given else None
         dx = torch.empty(T * N, In, device=dev, dtype=torch.float32) \
             if (ctx.needs_input_grad[1] and not gx_given) else None
-        drow = None
         # critical path (main stream): what the layers below / the callers wait for
         for d in range(ndir):
             w_ih = weights[4 * d]
             if dx is not None:                                             # dx (+)= dG W_ih
                 gemm(dg[d].view(T * N, 4 * Hd), w_ih[:, c0c:c1c], dx, T * N, In, 4 * Hd, b_kmajor=False,
                      accumulate=int(d > 0))
-        if rowbias is not None and ctx.needs_input_grad[4]:
+        if need_drow and drow is None:
             drow = torch.zeros(N, 4 * Hd, device=dev, dtype=torch.float32)
             for d in range(ndir):                                          # the term enters every direction
                 colsum_acc(dg[d].view(T, N * 4 * Hd), T, N * 4 * Hd, drow.view(-1))
