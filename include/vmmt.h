@@ -133,6 +133,12 @@ int vmmt_attention_fwd(const float* qp, const float* ctx, const int64_t* lengths
 int vmmt_attention_bwd(const float* dcvec, const float* qp, const float* ctx, const float* align,
                        const int64_t* lengths, float* dscore_ws /*[T,B,S]*/, float* dqp, float* dctx,
                        int accumulate_dctx, int T, int B, int S, int H, void* stream);
+/* the same in two launches: the query side (dscore, dqp: the decoder's backward chain waits for it) and the context side
+ * (dctx: only the encoders' backward reads it), so that the caller may put the latter on another stream */
+int vmmt_attention_bwd_query(const float* dcvec, const float* ctx, const float* align, const int64_t* lengths,
+                             float* dscore_ws, float* dqp, int T, int B, int S, int H, void* stream);
+int vmmt_attention_bwd_ctx(const float* dcvec, const float* qp, const float* align, const float* dscore_ws,
+                           float* dctx, int accumulate_dctx, int T, int B, int S, int H, void* stream);
 
 /* ---- inference networks (NormalVariationalEncoder.py:65-84, 12-43; Dists.py:21-26; VILoss.py:439-460) */
 /* x[t,b,k] at x + t*stride_t + b*stride_b + k: time-major [T,B,H] (stride_t = B*H, stride_b = H) or the transposed view of a

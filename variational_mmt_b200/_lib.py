@@ -64,6 +64,8 @@ SIGNATURES = {
     "vmmt_lstm_cell_fwd": (I, [P, P, P, P, P, P, P, I, I, P]),
     "vmmt_attention_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "vmmt_attention_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P]),
+    "vmmt_attention_bwd_query": (I, [P, P, P, P, P, P, I, I, I, I, P]),
+    "vmmt_attention_bwd_ctx": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "vmmt_masked_mean_fwd": (I, [P, L, L, P, P, L, I, I, I, P]),
     "vmmt_masked_mean_bwd": (I, [P, L, P, P, L, L, I, I, I, I, P]),
     "vmmt_act_bwd": (I, [P, P, P, L, I, P]),

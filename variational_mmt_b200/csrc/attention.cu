@@ -667,37 +667,48 @@ extern "C" int vmmt_attention_fwd(const float* qp, const float* ctx, const int64
   return vmmt_check_launch("attn_fwd_kernel");
 }
 
-extern "C" int vmmt_attention_bwd(const float* dcvec, const float* qp, const float* ctx,
-                                  const float* align, const int64_t* lengths, float* dscore_ws,
-                                  float* dqp, float* dctx, int accumulate_dctx, int T, int B, int S,
-                                  int H, void* stream) {
+// Backward in two launches: the QUERY side (d(scores) and dqp: what the decoder's backward chain waits for) and the CONTEXT
+// side (dctx: only the encoders' backward needs it).  vmmt_attention_bwd issues both on one stream; the two-entry form lets
+// the caller put the context side on another stream so that it does not sit between the query side and its consumer.
+extern "C" int vmmt_attention_bwd_query(const float* dcvec, const float* ctx, const float* align, const int64_t* lengths,
+                                        float* dscore_ws, float* dqp, int T, int B, int S, int H, void* stream) {
   VMMT_REQUIRE(S >= 1 && S <= SMAX, "attention_bwd: src_len %d outside [1,%d]", S, SMAX);
+  cudaStream_t st = (cudaStream_t)stream;
   if (!getenv("VMMT_ATTN_WARP")) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ntile = ceil_div(T, TT), nk = ceil_div(H, 64);
-    int rc1;
-    if (v2_ok(dcvec, ctx, T, S, H) && (reinterpret_cast<uintptr_t>(dqp) & 15) == 0) {
-      rc1 = launch_v2<1>(dcvec, ctx, lengths, const_cast<float*>(align), dscore_ws, dqp, T, B, S, H, st);
-    } else {
-      attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), st>>>(dcvec, ctx, align, lengths,
-                                                                                        dscore_ws, dqp, T, B, S, H, ntile);
-      rc1 = vmmt_check_launch("attn_bwd_query_tiled_kernel");
-    }
-    if (rc1) return rc1;
-    attn_bwd_ctx_tiled_kernel<<<B * nk, TILE_THREADS, 0, st>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H,
-                                                               accumulate_dctx, nk);
-    return vmmt_check_launch("attn_bwd_ctx_tiled_kernel");
+    if (v2_ok(dcvec, ctx, T, S, H) && (reinterpret_cast<uintptr_t>(dqp) & 15) == 0)
+      return launch_v2<1>(dcvec, ctx, lengths, const_cast<float*>(align), dscore_ws, dqp, T, B, S, H, st);
+    const int ntile = ceil_div(T, TT);
+    attn_bwd_query_tiled_kernel<<<B * ntile, TILE_THREADS, tiled_smem_bytes(S), st>>>(dcvec, ctx, align, lengths,
+                                                                                      dscore_ws, dqp, T, B, S, H, ntile);
+    return vmmt_check_launch("attn_bwd_query_tiled_kernel");
   }
   int tsplit = ceil_div(T, ATT_WARPS);
   const int want = ceil_div(2 * vmmt_num_sms(), B);
   if (tsplit > want) tsplit = want;
   if (tsplit < 1) tsplit = 1;
-  cudaStream_t s = (cudaStream_t)stream;
-  attn_bwd_query_kernel<<<B * tsplit, ATT_WARPS * 32, 0, s>>>(dcvec, ctx, align, lengths, dscore_ws,
-                                                              dqp, T, B, S, H, tsplit);
-  int rc = vmmt_check_launch("attn_bwd_query_kernel");
-  if (rc) return rc;
-  attn_bwd_ctx_kernel<<<S * B, 128, 0, s>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H,
-                                            accumulate_dctx);
+  attn_bwd_query_kernel<<<B * tsplit, ATT_WARPS * 32, 0, st>>>(dcvec, ctx, align, lengths, dscore_ws, dqp, T, B, S, H, tsplit);
+  return vmmt_check_launch("attn_bwd_query_kernel");
+}
+
+extern "C" int vmmt_attention_bwd_ctx(const float* dcvec, const float* qp, const float* align, const float* dscore_ws,
+                                      float* dctx, int accumulate_dctx, int T, int B, int S, int H, void* stream) {
+  VMMT_REQUIRE(S >= 1 && S <= SMAX, "attention_bwd: src_len %d outside [1,%d]", S, SMAX);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!getenv("VMMT_ATTN_WARP")) {
+    const int nk = ceil_div(H, 64);
+    attn_bwd_ctx_tiled_kernel<<<B * nk, TILE_THREADS, 0, st>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H,
+                                                               accumulate_dctx, nk);
+    return vmmt_check_launch("attn_bwd_ctx_tiled_kernel");
+  }
+  attn_bwd_ctx_kernel<<<S * B, 128, 0, st>>>(dcvec, qp, align, dscore_ws, dctx, T, B, S, H, accumulate_dctx);
   return vmmt_check_launch("attn_bwd_ctx_kernel");
+}
+
+extern "C" int vmmt_attention_bwd(const float* dcvec, const float* qp, const float* ctx,
+                                  const float* align, const int64_t* lengths, float* dscore_ws,
+                                  float* dqp, float* dctx, int accumulate_dctx, int T, int B, int S,
+                                  int H, void* stream) {
+  int rc = vmmt_attention_bwd_query(dcvec, ctx, align, lengths, dscore_ws, dqp, T, B, S, H, stream);
+  if (rc) return rc;
+  return vmmt_attention_bwd_ctx(dcvec, qp, align, dscore_ws, dctx, accumulate_dctx, T, B, S, H, stream);
 }

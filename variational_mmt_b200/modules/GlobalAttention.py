@@ -32,8 +32,11 @@ class GlobalAttention(nn.Module):
     def forward_time_major(self, q, context, context_lengths=None):
         """q [T,B,dim], context [S,B,dim] (both time-major) -> attn_h [T,B,dim], align [T,B,S]."""
         dim = self.dim
+        # (the join node is created BEFORE linear_in: autograd runs ready nodes in reverse creation order, so in backward
+        # linear_in's input-gradient GEMM is issued before the join makes the stream wait for the context-side kernel)
+        context, token = ops.attention_context(context)
         qp = ops.linear(q, self.linear_in.weight) if self.attn_type == "general" else q
-        cvec, align = ops.AttentionCoreFn.apply(qp, context, context_lengths)
+        cvec, align = ops.AttentionCoreFn.apply(qp, context, context_lengths, token)
         attn_h = ops.dual_linear(cvec, q, self.linear_out.weight, act=ops.ACT_TANH)     # tanh(linear_out([c ; q]))
         return attn_h, align
 

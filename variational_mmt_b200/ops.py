@@ -274,7 +274,7 @@ def _gx_stream(device):
 def aux_streams():
     """Every helper stream this module has created (side lanes, branch lanes, loss stream): what a consumer of ALL the
     gradients issued so far has to wait for."""
-    out = list(_side["streams"]) + list(_branch["streams"].values()) + list(_gx.values())
+    out = list(_side["streams"]) + list(_branch["streams"].values()) + list(_gx.values()) + list(_attn_fork.values())
     if _loss_stream is not None:
         out.append(_loss_stream)
     return out
@@ -794,11 +794,42 @@ def _rows(v):
     return v.as_strided((T * N, Hd), (v.stride(1), 1), v.storage_offset())
 
 
+class AttnJoinFn(Function):
+    """Identity on the attention context.  Its backward runs right after AttentionCoreFn.backward (it consumes that node's
+    context gradient) and makes the stream wait for the context-side kernel that AttentionCoreFn forked onto another
+    stream: the decoder's backward chain (query side -> linear_in backward -> recurrence) does not queue behind a kernel
+    only the encoders' backward needs."""
+
+    @staticmethod
+    def forward(ctx, context, token):
+        ctx.token = token
+        return context.view_as(context)
+
+    @staticmethod
+    def backward(ctx, g):
+        ev = ctx.token.pop("event", None)
+        if ev is not None:
+            torch.cuda.current_stream(g.device).wait_event(ev)
+        ctx.token.pop("keep", None)                       # the forked kernel's operands may be recycled from here on
+        return g, None
+
+
+def attention_context(context):
+    """-> (context', token) for AttentionCoreFn.apply(qp, context', lengths, token); token is None when nothing is forked."""
+    if context.is_cuda and context.requires_grad and torch.is_grad_enabled() and _branch["enabled"]:
+        token = {}
+        return AttnJoinFn.apply(context, token), token
+    return context, None
+
+
+_attn_fork = {}
+
+
 class AttentionCoreFn(Function):
     """scores + masked softmax + context (onmt/modules/GlobalAttention.py:108-113,169-184)."""
 
     @staticmethod
-    def forward(ctx, qp, context, lengths):
+    def forward(ctx, qp, context, lengths, token=None):
         qp, context = qp.contiguous(), context.contiguous()
         T, B, H = qp.shape
         S = context.shape[0]
@@ -807,6 +838,7 @@ class AttentionCoreFn(Function):
         L.call("vmmt_attention_fwd", fptr(qp), fptr(context), ptr(lengths), fptr(align), fptr(cvec),
                T, B, S, H, stream())
         ctx.save_for_backward(qp, context, align, lengths)
+        ctx.token = token
         ctx.mark_non_differentiable(align)
         return cvec, align
 
@@ -815,13 +847,31 @@ class AttentionCoreFn(Function):
         qp, context, align, lengths = ctx.saved_tensors
         T, B, H = qp.shape
         S = context.shape[0]
+        dev = qp.device
         dcvec = dcvec.contiguous()
-        ds = torch.empty(T, B, S, device=qp.device, dtype=torch.float32)
+        ds = torch.empty(T, B, S, device=dev, dtype=torch.float32)
         dqp = torch.empty_like(qp)
         dctx = torch.empty_like(context)
-        L.call("vmmt_attention_bwd", fptr(dcvec), fptr(qp), fptr(context), fptr(align), ptr(lengths),
-               fptr(ds), fptr(dqp), fptr(dctx), 0, T, B, S, H, stream())
-        return dqp, dctx, None
+        token = ctx.token
+        if token is None or not ctx.needs_input_grad[1]:
+            L.call("vmmt_attention_bwd", fptr(dcvec), fptr(qp), fptr(context), fptr(align), ptr(lengths),
+                   fptr(ds), fptr(dqp), fptr(dctx), 0, T, B, S, H, stream())
+            return dqp, dctx, None, None
+        # query side on this stream (the chain continues with it); context side on a forked stream, joined by AttnJoinFn
+        L.call("vmmt_attention_bwd_query", fptr(dcvec), fptr(context), fptr(align), ptr(lengths), fptr(ds), fptr(dqp),
+               T, B, S, H, stream())
+        cur = torch.cuda.current_stream(dev)
+        fork = _attn_fork.get(dev)
+        if fork is None:
+            fork = _attn_fork[dev] = torch.cuda.Stream(device=dev, priority=int(os.environ.get("VMMT_BRANCH_PRIO", "-1")))
+        fork.wait_stream(cur)
+        with torch.cuda.stream(fork):
+            L.call("vmmt_attention_bwd_ctx", fptr(dcvec), fptr(qp), fptr(align), fptr(ds), fptr(dctx), 0, T, B, S, H, stream())
+            ev = torch.cuda.Event()
+            ev.record(fork)
+        token["event"] = ev
+        token["keep"] = (dcvec, qp, align, ds, dctx)       # read / written on the forked stream until the join
+        return dqp, dctx, None, None
 
 
 class MaskedMeanFn(Function):
