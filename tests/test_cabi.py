@@ -124,3 +124,20 @@ def test_ctypes_signatures_match_header_prototypes():
         if want_r != got_r:
             bad.append(f"{name} return ('{ret}'): header {want_r}, ctypes {got_r}")
     assert not bad, "\n".join(bad)
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md (the reference-side binding guide) mentions every symbol include/vmmt.h declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "vmmt.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = []
+    for sym in sorted(set(re.findall(r"\b(vmmt_[a-z0-9_]+)\s*\(", header))):
+        if sym in doc:
+            continue
+        m = re.match(r"(vmmt_.*)_(fwd|bwd|wgrad)$", sym)
+        if m and any((m.group(1) + suf) in doc for suf in ("_fwd/bwd", "_*")):
+            continue
+        missing.append(sym)
+    assert not missing, missing
