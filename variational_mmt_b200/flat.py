@@ -1,7 +1,8 @@
 """One contiguous fp32 buffer for all parameters and one for all gradients.
 
 The backward kernels accumulate straight into ``param.grad`` views of the flat gradient buffer, so
-``zero_grad`` is one memset, the data-parallel exchange is one NCCL all-reduce and clip+Adam is two
+``zero_grad`` is one memset, the data-parallel exchange runs over the flat buffers (peer-memory kernels, or one NCCL
+all-reduce as the fallback) and clip+Adam is two
 launches (see Optim.py).  Parameter identity, names and shapes are untouched, so state_dicts saved
 by the reference load unchanged.
 """

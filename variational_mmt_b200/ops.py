@@ -117,10 +117,11 @@ def _anchor(device):
 # ---- side stream: weight / bias gradient GEMMs run off the critical path of the backward pass -------------------
 # The backward's critical path is the chain of recurrences (latency bound, ~110 of the 148 SMs lightly used) plus the
 # input-gradient GEMMs that feed the next layer down.  The weight-gradient GEMMs and bias column sums of every
-# Linear / LSTM layer only feed the optimiser, so they are issued on ONE side stream (hence serialised among
-# themselves: two of them may accumulate into slices of the same parameter) that forks from the main stream after
-# the tensors they read are complete, and is joined before the gradients are consumed (end of the backward pass /
-# Optim.step).  Under CUDA-graph capture the fork / join become graph edges.
+# Linear / LSTM layer only feed the optimiser, so they are issued on lowest-priority side streams ("lanes": the launches
+# of one block stay on one lane, hence serialised among themselves -- two of them may accumulate into slices of the same
+# parameter) that fork from the main stream after the tensors they read are complete, and are joined before the
+# gradients are consumed (end of the backward pass / Optim.step).  Under CUDA-graph capture the fork / join become
+# graph edges.  (LSTM bias gradients are not among them any more: the BPTT kernel sums them itself.)
 _side = {"streams": [], "keep": [], "dirty": False, "enabled": True, "next": 0,
          "lanes": int(os.environ.get("VMMT_SIDE_LANES", "4"))}
 
